@@ -1,0 +1,701 @@
+// FP8 paged decode attention, q-per-token/per-head scale, k/v per-tensor scale, dynamic split-k
+// task map. B200 (sm_100a) design, written from scratch:
+//
+//   * persistent grid = num_total_ctas (one CTA per SM); each CTA walks its bin of the task map
+//   * warp 0  : TMA producer  - K/V 64-token pages -> 128B-swizzled smem ring (12 x 16 KB slots),
+//                               Q rows of the task -> smem (double buffered)
+//   * warp 1  : tcgen05 issuer - S^T[128 keys, NQ] = K_tile . Q^T     (kind::f8f6f4, K-major A/B)
+//                                O^T[128 d, NQ]   = V_tile^T . P^T    (MN-major A and B: V is
+//                                consumed exactly as it lies in the cache, no byte transpose)
+//   * warps 2-5: softmax      - one thread per key: TMEM->regs, scale/mask, online softmax in the
+//                               log2 domain, P*256 -> e4m3 -> smem, O tile TMEM->regs accumulate
+//   accumulators live in TMEM (S^T and O^T double buffered, 4*NQ columns).
+//
+// Semantics follow reference
+//   src/attention/decode/sm90/dynamic/smallm_fp8_qpertoken_perhead_kvpertensor_dim128_dynamic_splitk_kernels.cuh:29-437
+//   src/attention/decode/sm90/util_kernels.cuh:280-305 (mask), :332-436 (online softmax),
+//   :523-602 (final), :638-660 (lse)
+// and the launcher contract of
+//   src/attention/decode/decode.h:28-37 (attention_decode_fp8_async).
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace b200 {
+namespace decode {
+
+constexpr int kTileN = 128;  // keys per tile == UMMA M
+constexpr int kPage = 64;    // paged block size (tokens)
+constexpr int kD = 128;      // head dim
+constexpr int kSlotBytes = kTileN * kD;  // 16 KB (fp8)
+constexpr int kNumSlots = 12;
+constexpr int kThreads = 192;
+constexpr int kTaskStride = 12;
+constexpr int kSoftmaxBar = 1;
+
+struct Params {
+  const int* task_map;
+  const int* block_ids;
+  const float* qscale;
+  const float* kscale;
+  const float* vscale;
+  float* split_out;
+  float* lse;
+  int num_batch;
+  int num_seq_q;
+  int num_head_q;
+  int num_head_kv;
+  int group;
+  int num_seq_max_blocks;
+  int qscale_stride;
+  int max_splitk;
+  int lse_pad;
+  int k_head_first;  // TMA dim order of the cache maps: (d, head, token, blk) or (d, token, head, blk)
+  int v_head_first;
+  float softmax_scale_log2;
+};
+
+struct Task {
+  int ihead_kv, ibatch, ichunk, iseq_start;
+  int num_seqkv, num_seqkvcache, num_tile_kv, num_tile_full;
+  int is_causal;
+};
+
+__device__ __forceinline__ bool load_task(const int* row, Task& t) {
+  int4 a = *reinterpret_cast<const int4*>(row);
+  if (a.x < 0 || a.y < 0) return false;
+  int4 b = *reinterpret_cast<const int4*>(row + 4);
+  int c = row[8];
+  t.ihead_kv = a.x;
+  t.ibatch = a.y;
+  t.ichunk = a.z;
+  t.iseq_start = a.w;
+  t.num_seqkv = b.x;
+  t.num_seqkvcache = b.y;
+  t.num_tile_kv = b.z;
+  t.num_tile_full = b.w;
+  t.is_causal = c;
+  return true;
+}
+
+template <int NQ>
+struct Smem {
+  static constexpr int kQBytes = NQ * kD;            // one Q buffer (SW128 rows of 128 B)
+  static constexpr int kPPlanes = NQ / 16;
+  static constexpr int kPBytes = kPPlanes * kTileN * 16;  // one P buffer
+  static constexpr int kOffSlots = 0;
+  static constexpr int kOffQ = kNumSlots * kSlotBytes;
+  static constexpr int kOffP = kOffQ + 2 * 4096;  // Q buffers padded to 4 KB (1024-B aligned)
+  static constexpr int kOffMax = kOffP + 2 * kPBytes;
+  static constexpr int kOffBar = kOffMax + 2 * 4 * 32 * 4;
+  static constexpr int kNumBars = 2 * kNumSlots + 16;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kTotal = kOffTmem + 16;
+};
+
+template <int NQ, int RL>
+__global__ void __launch_bounds__(kThreads, 1)
+    decode_attn_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                           const __grid_constant__ CUtensorMap tmap_k,
+                           const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+  using L = Smem<NQ>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  uint8_t* slots = smem + L::kOffSlots;
+  uint8_t* q_smem = smem + L::kOffQ;
+  uint8_t* p_smem = smem + L::kOffP;
+  float* smax = reinterpret_cast<float*>(smem + L::kOffMax);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
+
+  uint64_t* slot_full = bars;
+  uint64_t* slot_empty = bars + kNumSlots;
+  uint64_t* q_full = bars + 2 * kNumSlots;
+  uint64_t* q_empty = q_full + 2;
+  uint64_t* s_full = q_full + 4;
+  uint64_t* s_empty = q_full + 6;
+  uint64_t* p_full = q_full + 8;
+  uint64_t* p_empty = q_full + 10;
+  uint64_t* o_full = q_full + 12;
+  uint64_t* o_empty = q_full + 14;
+  static_assert(L::kNumBars >= 2 * kNumSlots + 16, "barrier count");
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  // ---- one-time setup --------------------------------------------------------------------
+  {
+    // zero both Q buffers so padded query rows are exact zeros for the whole kernel
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * 4096 / 16; i += kThreads) {
+      reinterpret_cast<uint4*>(q_smem)[i] = z;
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_k);
+    prefetch_tensormap(&tmap_v);
+    for (int i = 0; i < kNumSlots; i++) {
+      mbar_init(&slot_full[i], 1);
+      mbar_init(&slot_empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ntpc1 = p.task_map[0];
+  const int* bin = p.task_map + (1 + static_cast<long long>(blockIdx.x) * ntpc1) * kTaskStride;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================================
+    const uint64_t pol_stream = make_policy_evict_first();
+    uint32_t j = 0;      // kv slot counter (K of tile n -> 2n, V -> 2n+1)
+    uint32_t qcnt = 0;   // task counter for the Q double buffer
+    Task t;
+    for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+      if (lane == 0) {
+        const int qb = qcnt & 1;
+        mbar_wait(&q_empty[qb], ((qcnt >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], p.num_seq_q * p.group * kD);
+        tma_load_3d(q_smem + qb * 4096, &tmap_q, &q_full[qb], 0, t.ihead_kv * p.group,
+                    t.ibatch * p.num_seq_q);
+      }
+      qcnt++;
+      const int nblk = (t.num_seqkv + kPage - 1) / kPage;
+      const int* ids = p.block_ids + static_cast<long long>(t.ibatch) * p.num_seq_max_blocks +
+                       t.iseq_start / kPage;
+      const int ntiles = t.num_tile_kv;
+      const int kc1 = p.k_head_first ? t.ihead_kv : 0;
+      const int kc2 = p.k_head_first ? 0 : t.ihead_kv;
+      const int vc1 = p.v_head_first ? t.ihead_kv : 0;
+      const int vc2 = p.v_head_first ? 0 : t.ihead_kv;
+      for (int g0 = 0; g0 < ntiles; g0 += 16) {
+        int bi = g0 * 2 + lane;
+        bi = bi < nblk ? bi : nblk - 1;
+        const int my_id = __ldg(ids + bi);
+        const int gt = (ntiles - g0) < 16 ? (ntiles - g0) : 16;
+        for (int tt = 0; tt < gt; tt++) {
+          const int id0 = __shfl_sync(0xffffffffu, my_id, 2 * tt);
+          const int id1 = __shfl_sync(0xffffffffu, my_id, 2 * tt + 1);
+          if (lane == 0) {
+            {
+              const uint32_t s = j % kNumSlots;
+              mbar_wait(&slot_empty[s], ((j / kNumSlots) & 1) ^ 1);
+              mbar_arrive_expect_tx(&slot_full[s], kSlotBytes);
+              uint8_t* dst = slots + s * kSlotBytes;
+              tma_load_4d_hint(dst, &tmap_k, &slot_full[s], 0, kc1, kc2, id0, pol_stream);
+              tma_load_4d_hint(dst + kSlotBytes / 2, &tmap_k, &slot_full[s], 0, kc1, kc2, id1,
+                               pol_stream);
+            }
+            {
+              const uint32_t s = (j + 1) % kNumSlots;
+              mbar_wait(&slot_empty[s], (((j + 1) / kNumSlots) & 1) ^ 1);
+              mbar_arrive_expect_tx(&slot_full[s], kSlotBytes);
+              uint8_t* dst = slots + s * kSlotBytes;
+              tma_load_4d_hint(dst, &tmap_v, &slot_full[s], 0, vc1, vc2, id0, pol_stream);
+              tma_load_4d_hint(dst + kSlotBytes / 2, &tmap_v, &slot_full[s], 0, vc1, vc2, id1,
+                               pol_stream);
+            }
+          }
+          j += 2;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== tcgen05 issuer ==========================================
+    constexpr uint32_t idesc_qk = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 1, 1);
+    const uint32_t slots_addr = smem_u32(slots);
+    const uint32_t q_addr = smem_u32(q_smem);
+    const uint32_t p_addr = smem_u32(p_smem);
+
+    auto issue_pv = [&](uint32_t m) {
+      const uint32_t jv = 2 * m + 1;
+      const uint32_t s = jv % kNumSlots;
+      const uint32_t buf = m & 1;
+      const uint32_t ph = (m >> 1) & 1;
+      mbar_wait(&p_full[buf], ph);
+      mbar_wait(&slot_full[s], (jv / kNumSlots) & 1);
+      mbar_wait(&o_empty[buf], ph ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t va = slots_addr + s * kSlotBytes;
+        const uint32_t pa = p_addr + buf * L::kPBytes;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // A = V tile as stored ([key][d], d contiguous): MN-major, 128B swizzle,
+          //     8-key groups 1024 B apart; one MMA consumes 32 keys = 4096 B.
+          const uint64_t ad = make_smem_desc(va + k * 4096, 16, 1024, kLayoutSW128);
+          // B = P^T ([key][16 queries] planes): MN-major, no swizzle; 8-key core matrices are
+          //     128 B apart (LBO), the second 16-query plane is kTileN*16 B away (SBO).
+          const uint64_t bd = make_smem_desc(pa + k * 512, 128, kTileN * 16, kLayoutNone);
+          umma_f8(tmem_base + 2 * NQ + buf * NQ, ad, bd, idesc_pv, k > 0);
+        }
+        umma_commit(&slot_empty[s]);
+        umma_commit(&p_empty[buf]);
+        umma_commit(&o_full[buf]);
+      }
+      __syncwarp();
+    };
+
+    uint32_t n = 0;
+    uint32_t qcnt = 0;
+    Task t;
+    for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+      const int qb = qcnt & 1;
+      mbar_wait(&q_full[qb], (qcnt >> 1) & 1);
+      const int ntiles = t.num_tile_kv;
+      for (int tt = 0; tt < ntiles; tt++) {
+        const uint32_t jk = 2 * n;
+        const uint32_t s = jk % kNumSlots;
+        const uint32_t buf = n & 1;
+        mbar_wait(&slot_full[s], (jk / kNumSlots) & 1);
+        mbar_wait(&s_empty[buf], ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t ka = slots_addr + s * kSlotBytes;
+          const uint32_t qa = q_addr + qb * 4096;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart; K advances 32 B.
+            const uint64_t ad = make_smem_desc(ka + k * 32, 16, 1024, kLayoutSW128);
+            const uint64_t bd = make_smem_desc(qa + k * 32, 16, 1024, kLayoutSW128);
+            umma_f8(tmem_base + buf * NQ, ad, bd, idesc_qk, k > 0);
+          }
+          umma_commit(&slot_empty[s]);
+          umma_commit(&s_full[buf]);
+          if (tt == ntiles - 1) umma_commit(&q_empty[qb]);
+        }
+        __syncwarp();
+        if (n > 0) issue_pv(n - 1);
+        n++;
+      }
+      qcnt++;
+    }
+    if (n > 0) issue_pv(n - 1);
+  } else {
+    // =========================== softmax / epilogue warps =================================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;  // key index (S^T) and d index (O^T)
+    const int sw = warp - 2;             // 0..3 index for smem exchange
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float kscale = p.kscale[0];
+    const float out_scale = p.vscale[0] * (1.0f / 256.0f);
+
+    uint32_t n = 0;
+    Task t;
+    for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+      float c[RL], mrun[RL], lrun[RL], alpha_pend[RL];
+      float acc[RL];
+      {
+        const float* qs = p.qscale +
+                          static_cast<long long>(t.ibatch) * p.num_seq_q * p.qscale_stride +
+                          t.ihead_kv * p.group;
+#pragma unroll
+        for (int r = 0; r < RL; r++) {
+          const int sq = r / p.group;
+          const int g = r - sq * p.group;
+          const bool valid = sq < p.num_seq_q;
+          const float qv = valid ? __ldg(qs + sq * p.qscale_stride + g) : 0.f;
+          c[r] = qv * kscale * p.softmax_scale_log2;
+          mrun[r] = -INFINITY;
+          lrun[r] = 0.f;
+          alpha_pend[r] = 1.f;
+          acc[r] = 0.f;
+        }
+      }
+      const int lim_len = t.num_seqkv;
+      const int lim_causal = t.num_seqkvcache;
+      const int ntiles = t.num_tile_kv;
+
+      auto consume_o = [&](uint32_t m) {
+        const uint32_t buf = m & 1;
+        mbar_wait(&o_full[buf], (m >> 1) & 1);
+        tc_fence_after();
+        uint32_t o[NQ];
+        if constexpr (NQ == 16) {
+          tmem_ld_x16(lane_addr + 2 * NQ + buf * NQ, o);
+        } else {
+          tmem_ld_x32(lane_addr + 2 * NQ + buf * NQ, o);
+        }
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&o_empty[buf]);
+#pragma unroll
+        for (int r = 0; r < RL; r++) {
+          acc[r] = acc[r] * alpha_pend[r] + __uint_as_float(o[r]);
+        }
+      };
+
+      for (int tt = 0; tt < ntiles; tt++) {
+        const uint32_t buf = n & 1;
+        const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&s_full[buf], ph);
+        tc_fence_after();
+        uint32_t sraw[NQ];
+        if constexpr (NQ == 16) {
+          tmem_ld_x16(lane_addr + buf * NQ, sraw);
+        } else {
+          tmem_ld_x32(lane_addr + buf * NQ, sraw);
+        }
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&s_empty[buf]);
+
+        const int key = tt * kTileN + row_in_tile;
+        const int lim_min = lim_len < lim_causal ? lim_len : lim_causal;
+        const bool need_mask = (tt + 1) * kTileN > lim_min;
+        float x[RL];
+        float* mx = smax + (buf * 4 + sw) * 32;
+#pragma unroll
+        for (int r = 0; r < RL; r++) {
+          float v = __uint_as_float(sraw[r]) * c[r];
+          if (need_mask) {
+            const int sq = r / p.group;
+            const bool dead = (key >= lim_len) || (key > lim_causal + sq);
+            v = dead ? -INFINITY : v;
+          }
+          x[r] = v;
+          const float wm = warp_max_f32(v);
+          if (lane == 0) mx[r] = wm;
+        }
+        named_bar_sync(kSoftmaxBar, 128);
+        const float* mall = smax + buf * 4 * 32;
+        float pv[RL];
+#pragma unroll
+        for (int r = 0; r < RL; r++) {
+          const float tm = fmaxf(fmaxf(mall[r], mall[32 + r]), fmaxf(mall[64 + r], mall[96 + r]));
+          const float mold = mrun[r];
+          const float mnew = fmaxf(mold, tm);
+          float a = 1.f, e = 0.f;
+          if (mnew != -INFINITY) {
+            a = exp2_approx(mold - mnew);
+            e = exp2_approx(x[r] - mnew);
+          }
+          mrun[r] = mnew;
+          lrun[r] = lrun[r] * a + e;
+          pv[r] = e * 256.f;
+          // alpha for the O tile of *this* key tile is applied when that tile is consumed
+          x[r] = a;
+        }
+        // ---- P^T row of this key -> smem (e4m3), 16 queries per plane ----
+        mbar_wait(&p_empty[buf], ph ^ 1);
+        {
+          uint8_t* pb = p_smem + buf * L::kPBytes + row_in_tile * 16;
+#pragma unroll
+          for (int pl = 0; pl < L::kPPlanes; pl++) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const int r = pl * 16 + i;
+              f[i] = (r < RL) ? pv[r < RL ? r : 0] : 0.f;
+            }
+            uint4 w;
+            w.x = cvt_e4m3x4(f[0], f[1], f[2], f[3]);
+            w.y = cvt_e4m3x4(f[4], f[5], f[6], f[7]);
+            w.z = cvt_e4m3x4(f[8], f[9], f[10], f[11]);
+            w.w = cvt_e4m3x4(f[12], f[13], f[14], f[15]);
+            *reinterpret_cast<uint4*>(pb + pl * kTileN * 16) = w;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[buf]);
+
+        if (tt > 0) consume_o(n - 1);
+#pragma unroll
+        for (int r = 0; r < RL; r++) alpha_pend[r] = x[r];
+        n++;
+      }
+      if (ntiles > 0) consume_o(n - 1);
+
+      // ---- task epilogue: 1/sum, v scale, partial O and LSE out ----
+      float* red = smax;  // reuse: [4 warps][32]
+      named_bar_sync(kSoftmaxBar, 128);
+#pragma unroll
+      for (int r = 0; r < RL; r++) {
+        const float ws = warp_sum_f32(lrun[r]);
+        if (lane == 0) red[sw * 32 + r] = ws;
+      }
+      named_bar_sync(kSoftmaxBar, 128);
+      const long long chunk_row =
+          static_cast<long long>(t.ibatch) * p.max_splitk + t.ichunk;
+#pragma unroll
+      for (int r = 0; r < RL; r++) {
+        const int sq = r / p.group;
+        const int g = r - sq * p.group;
+        if (sq < p.num_seq_q) {
+          const float tot = red[r] + red[32 + r] + red[64 + r] + red[96 + r];
+          const float inv = tot != 0.f ? rcp_approx(tot) : 0.f;
+          const long long orow =
+              (chunk_row * p.num_seq_q + sq) * p.num_head_q + t.ihead_kv * p.group + g;
+          p.split_out[orow * kD + row_in_tile] = acc[r] * inv * out_scale;
+          if (row_in_tile == r) {
+            const float l = (mrun[r] == -INFINITY) ? -INFINITY : mrun[r] + log2_approx(tot);
+            p.lse[((chunk_row * p.num_head_kv + t.ihead_kv) * p.num_seq_q + sq) * p.lse_pad + g] =
+                l;
+          }
+        }
+      }
+      named_bar_sync(kSoftmaxBar, 128);  // red[] reused as smax by the next task
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-k combine: y = sum_c 2^(lse_c - m) O_c / sum_c 2^(lse_c - m)  -> bf16
+// (reference src/attention/decode/splitk_combine_kernels.cuh:140-322)
+// one 128-thread block per output row (b, s, hq); warp w handles chunks w, w+4, ...
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    decode_combine_kernel(__nv_bfloat16* __restrict__ y, const float* __restrict__ split_out,
+                          const float* __restrict__ lse, const int* __restrict__ task_map,
+                          int num_batch, int num_seq_q, int num_head_q, int num_head_kv, int group,
+                          int max_splitk, int lse_pad, int ldY) {
+  __shared__ float4 s_acc[4][32];
+  __shared__ float s_m[4];
+  __shared__ float s_l[4];
+
+  const int row = blockIdx.x;  // (b * Sq + s) * Hq + hq
+  const int hq = row % num_head_q;
+  const int bs = row / num_head_q;
+  const int s = bs % num_seq_q;
+  const int b = bs / num_seq_q;
+  const int hkv = hq / group;
+  const int g = hq - hkv * group;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int ntpc1 = task_map[0];
+  const int nctas = task_map[1];
+  const int max_batch = task_map[3];
+  (void)max_batch;
+  const int* chunk_table = task_map + kTaskStride * (ntpc1 * nctas + 1);
+  const int nchunks = chunk_table[hkv * num_batch + b];
+
+  float m = -INFINITY;
+  float l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = warp; c < nchunks; c += 4) {
+    const long long chunk_row = static_cast<long long>(b) * max_splitk + c;
+    const float lc = __ldg(lse + ((chunk_row * num_head_kv + hkv) * num_seq_q + s) * lse_pad + g);
+    const float4 o = ld_nc_f4(split_out +
+                              ((chunk_row * num_seq_q + s) * num_head_q + hq) * (long long)kD +
+                              lane * 4);
+    if (lc == -INFINITY) continue;
+    const float mn = fmaxf(m, lc);
+    const float a = exp2_approx(m - mn);
+    const float w = exp2_approx(lc - mn);
+    acc.x = acc.x * a + o.x * w;
+    acc.y = acc.y * a + o.y * w;
+    acc.z = acc.z * a + o.z * w;
+    acc.w = acc.w * a + o.w * w;
+    l = l * a + w;
+    m = mn;
+  }
+  s_acc[warp][lane] = acc;
+  if (lane == 0) {
+    s_m[warp] = m;
+    s_l[warp] = l;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float mg = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      const float sc = (s_m[w] == -INFINITY) ? 0.f : exp2_approx(s_m[w] - mg);
+      const float4 a = s_acc[w][lane];
+      r.x += a.x * sc;
+      r.y += a.y * sc;
+      r.z += a.z * sc;
+      r.w += a.w * sc;
+      lt += s_l[w] * sc;
+    }
+    const float inv = lt > 0.f ? 1.f / lt : 0.f;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(r.x * inv, r.y * inv);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(r.z * inv, r.w * inv);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    __nv_bfloat16* dst = y + static_cast<long long>(bs) * ldY + hq * kD + lane * 4;
+    *reinterpret_cast<uint2*>(dst) = pk;
+  }
+}
+
+template <int NQ, int RL>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const Params& p, int grid, cudaStream_t stream) {
+  using L = Smem<NQ>;
+  auto kern = decode_attn_fp8_kernel<NQ, RL>;
+  static bool configured = false;
+  if (!configured) {
+    HPC_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  kern<<<grid, kThreads, L::kTotal, stream>>>(tq, tk, tv, p);
+  HPC_CUDA_CHECK(cudaGetLastError());
+  return HPC_OK;
+}
+
+}  // namespace decode
+}  // namespace b200
+
+using namespace b200;  // NOLINT
+
+extern "C" int hpc_attention_decode_fp8_async(
+    void* y_ptr, void* lse_ptr, void* split_out_ptr, const int* task_map_ptr, const void* q_ptr,
+    void* kcache_ptr, void* vcache_ptr, const int* block_ids_ptr, const int* num_seq_kvcache_ptr,
+    const float* qscale_ptr, const float* kscale_ptr, const float* vscale_ptr, int* split_flag_ptr,
+    int new_kv_included, int splitk, int splitk_min_len, int consumers, int quant_type,
+    int num_batch, int num_seq_q, int num_head_q, int num_head_k, int num_head_v, int num_dim_qk,
+    int num_dim_v, int num_kvcache_blocks, int block_size, int num_seq_max_blocks,
+    int qscale_pad_stride, int ldY, int ldQ, int64_t kcache_block_stride,
+    int64_t kcache_token_stride, int64_t kcache_head_stride, int64_t vcache_block_stride,
+    int64_t vcache_token_stride, int64_t vcache_head_stride, cudaStream_t stream) {
+  (void)num_seq_kvcache_ptr;  // lengths come from the task map (as in the reference dynamic path)
+  (void)split_flag_ptr;
+  (void)new_kv_included;
+  (void)splitk_min_len;
+  (void)consumers;
+  HPC_REQUIRE(quant_type == 1,
+              "attention_decode_fp8: only quant_type 1 (q per-token/head, k/v per-tensor) is "
+              "implemented in this build, got %d",
+              quant_type);
+  HPC_REQUIRE(task_map_ptr != nullptr, "attention_decode_fp8: a task_map is required on sm_100");
+  HPC_REQUIRE(num_dim_qk == 128 && num_dim_v == 128, "head dim must be 128");
+  HPC_REQUIRE(block_size == 64, "kvcache paged blocksize must be 64");
+  HPC_REQUIRE(num_head_k == num_head_v && num_head_k > 0 && num_head_q % num_head_k == 0,
+              "bad head counts q=%d k=%d v=%d", num_head_q, num_head_k, num_head_v);
+  const int group = num_head_q / num_head_k;
+  const int rows = group * num_seq_q;
+  HPC_REQUIRE(rows >= 1 && rows <= 32 && group <= 16,
+              "heads_per_group * num_seq_q = %d not in [1, 32]", rows);
+  HPC_REQUIRE(splitk >= 1, "splitk (max chunks) must be >= 1");
+  HPC_REQUIRE((reinterpret_cast<uintptr_t>(q_ptr) & 15) == 0 && (ldQ % 16) == 0,
+              "q must be 16-byte aligned");
+  HPC_REQUIRE((kcache_block_stride % 16) == 0 && (kcache_token_stride % 16) == 0 &&
+                  (kcache_head_stride % 16) == 0 && (vcache_block_stride % 16) == 0 &&
+                  (vcache_token_stride % 16) == 0 && (vcache_head_stride % 16) == 0,
+              "kv cache strides must be multiples of 16 bytes");
+
+  CUtensorMap tq, tk, tv;
+  {
+    uint64_t dims[3] = {128, static_cast<uint64_t>(num_head_q),
+                        static_cast<uint64_t>(num_batch) * num_seq_q};
+    uint64_t strides[2] = {128, static_cast<uint64_t>(ldQ)};
+    uint32_t box[3] = {128, static_cast<uint32_t>(group), static_cast<uint32_t>(num_seq_q)};
+    int rc = encode_tmap_u8(&tq, q_ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  auto encode_cache = [&](CUtensorMap* tm, const void* base, int heads, int64_t blk_stride,
+                          int64_t tok_stride, int64_t head_stride, int* head_first) -> int {
+    // TMA wants strides ordered ascending: pick (d, head, token, blk) for NHD caches and
+    // (d, token, head, blk) for HND caches; the smem image of the 64x128 box is identical.
+    *head_first = head_stride <= tok_stride ? 1 : 0;
+    uint64_t dims[4];
+    uint64_t strides[3];
+    uint32_t box[4];
+    dims[0] = 128;
+    box[0] = 128;
+    if (*head_first) {
+      dims[1] = static_cast<uint64_t>(heads);
+      dims[2] = 64;
+      strides[0] = static_cast<uint64_t>(head_stride);
+      strides[1] = static_cast<uint64_t>(tok_stride);
+      box[1] = 1;
+      box[2] = 64;
+    } else {
+      dims[1] = 64;
+      dims[2] = static_cast<uint64_t>(heads);
+      strides[0] = static_cast<uint64_t>(tok_stride);
+      strides[1] = static_cast<uint64_t>(head_stride);
+      box[1] = 64;
+      box[2] = 1;
+    }
+    dims[3] = static_cast<uint64_t>(num_kvcache_blocks);
+    strides[2] = static_cast<uint64_t>(blk_stride);
+    box[3] = 1;
+    return encode_tmap_u8(tm, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  int k_head_first = 1, v_head_first = 1;
+  {
+    int rc = encode_cache(&tk, kcache_ptr, num_head_k, kcache_block_stride, kcache_token_stride,
+                          kcache_head_stride, &k_head_first);
+    if (rc) return rc;
+    rc = encode_cache(&tv, vcache_ptr, num_head_v, vcache_block_stride, vcache_token_stride,
+                      vcache_head_stride, &v_head_first);
+    if (rc) return rc;
+  }
+
+  decode::Params p;
+  p.task_map = task_map_ptr;
+  p.block_ids = block_ids_ptr;
+  p.qscale = qscale_ptr;
+  p.kscale = kscale_ptr;
+  p.vscale = vscale_ptr;
+  p.split_out = static_cast<float*>(split_out_ptr);
+  p.lse = static_cast<float*>(lse_ptr);
+  p.num_batch = num_batch;
+  p.num_seq_q = num_seq_q;
+  p.num_head_q = num_head_q;
+  p.num_head_kv = num_head_k;
+  p.group = group;
+  p.num_seq_max_blocks = num_seq_max_blocks;
+  p.qscale_stride = qscale_pad_stride;
+  p.max_splitk = splitk;
+  p.lse_pad = (group + 7) / 8 * 8;
+  p.k_head_first = k_head_first;
+  p.v_head_first = v_head_first;
+  p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(num_dim_qk));
+
+  const int grid = splitk;  // == num_total_ctas of the task map
+  int rc;
+  if (rows <= 4) {
+    rc = decode::launch_attn<16, 4>(tq, tk, tv, p, grid, stream);
+  } else if (rows <= 8) {
+    rc = decode::launch_attn<16, 8>(tq, tk, tv, p, grid, stream);
+  } else if (rows <= 12) {
+    rc = decode::launch_attn<16, 12>(tq, tk, tv, p, grid, stream);
+  } else if (rows <= 16) {
+    rc = decode::launch_attn<16, 16>(tq, tk, tv, p, grid, stream);
+  } else if (rows <= 24) {
+    rc = decode::launch_attn<32, 24>(tq, tk, tv, p, grid, stream);
+  } else {
+    rc = decode::launch_attn<32, 32>(tq, tk, tv, p, grid, stream);
+  }
+  if (rc) return rc;
+
+  const int out_rows = num_batch * num_seq_q * num_head_q;
+  decode::decode_combine_kernel<<<out_rows, 128, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(y_ptr), p.split_out, p.lse, task_map_ptr, num_batch, num_seq_q,
+      num_head_q, num_head_k, group, splitk, p.lse_pad, ldY);
+  HPC_CUDA_CHECK(cudaGetLastError());
+  return HPC_OK;
+}

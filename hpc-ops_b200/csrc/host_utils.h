@@ -1,0 +1,46 @@
+// Host-side helpers shared by the C-ABI launchers: error reporting, device queries, TMA descriptors.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/hpc_b200.h"
+
+namespace b200 {
+
+void set_last_error(const char* fmt, ...);
+
+#define HPC_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      b200::set_last_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,          \
+                           cudaGetErrorString(_e));                                       \
+      return HPC_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define HPC_REQUIRE(cond, ...)             \
+  do {                                     \
+    if (!(cond)) {                         \
+      b200::set_last_error(__VA_ARGS__);   \
+      return HPC_ERR_UNSUPPORTED;          \
+    }                                      \
+  } while (0)
+
+int sm_count();
+
+// Encode a tiled TMA descriptor (uint8 elements). dims/strides innermost-first; strides in bytes for
+// dims 1..rank-1. Returns 0 on success.
+int encode_tmap_u8(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+// Same for 2-byte and 4-byte element types.
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, const void* base,
+                int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                CUtensorMapSwizzle swizzle);
+
+}  // namespace b200

@@ -1,0 +1,76 @@
+"""ctypes binding of the C-ABI library (include/hpc_b200.h).
+
+The library is the product: if `_C.so` is missing or a launcher reports an error this module
+raises — there is no CPU or PyTorch fallback anywhere in `hpc`.
+"""
+import ctypes
+from pathlib import Path
+
+import torch
+
+_pkg_dir = Path(__file__).parent
+
+_so_files = list(_pkg_dir.glob("_C*.so"))
+if len(_so_files) != 1:
+    raise ImportError(
+        f"hpc (B200 build): expected exactly one _C*.so next to {__file__}, found "
+        f"{len(_so_files)}. Build it with `python hpc-ops_b200/build.py` (needs nvcc, sm_100a)."
+    )
+lib = ctypes.CDLL(str(_so_files[0]))
+
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_u32 = ctypes.c_uint32
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+
+lib.hpc_last_error.restype = ctypes.c_char_p
+lib.hpc_version.restype = ctypes.c_char_p
+lib.hpc_built_json.restype = ctypes.c_char_p
+lib.hpc_sm_count.restype = c_int
+
+lib.hpc_assign_attention_decode_task_host_bytes.restype = c_i64
+lib.hpc_assign_attention_decode_task_host_bytes.argtypes = [c_ptr] + [c_int] * 7
+lib.hpc_assign_attention_decode_task_sync.restype = c_int
+lib.hpc_assign_attention_decode_task_sync.argtypes = [c_ptr] + [c_int] * 7 + [c_ptr, c_i64]
+lib.hpc_assign_attention_decode_task_async.restype = c_int
+lib.hpc_assign_attention_decode_task_async.argtypes = [c_ptr, c_ptr] + [c_int] * 7 + [c_ptr]
+
+lib.hpc_attention_decode_fp8_async.restype = c_int
+lib.hpc_attention_decode_fp8_async.argtypes = (
+    [c_ptr] * 13 + [c_int] * 18 + [c_i64] * 6 + [c_ptr]
+)
+
+lib.hpc_selftest_umma_f8.restype = c_int
+lib.hpc_selftest_umma_f8.argtypes = (
+    [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]
+)
+
+
+def check(rc: int, what: str = ""):
+    """Turn a launcher status into the RuntimeError the reference raises via TORCH_CHECK."""
+    if rc != 0:
+        msg = lib.hpc_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"hpc {what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Raw data pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t) -> int:
+    """cudaStream_t of torch's current stream on the tensor's device."""
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_sm_count_cache = {}
+
+
+def sm_count(device=None) -> int:
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    if dev not in _sm_count_cache:
+        _sm_count_cache[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _sm_count_cache[dev]

@@ -1,0 +1,112 @@
+"""Generate the golden fixtures in tests/golden/ from the REFERENCE's own code.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+    python tests/golden/make_golden.py
+
+* attention: the reference keeps its ground truth as pure-torch functions inside its test files.
+  Those files `import hpc` at module level (needs their CUDA build), so we AST-extract the
+  reference function's source text and exec it unmodified on CPU tensors.
+* task map: outputs of the real reference CPU scheduler compiled in place (oracle/_ref, see
+  oracle/Makefile `make ref`). Pad ints 9..11 of each row are uninitialised stack bytes in the
+  reference (assign_task.cu:424 `TaskScheduleInfo task_info;`) and are stored zeroed.
+"""
+import ast
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[2]
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+from oracle import attention as oa  # noqa: E402
+from oracle import taskmap as otm  # noqa: E402
+
+
+def extract(path: Path, name: str):
+    src = path.read_text()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            code = ast.get_source_segment(src, node)
+            ns = {"torch": torch, "math": math, "F": torch.nn.functional}
+            exec(compile(code, str(path), "exec"), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
+def u8(t):
+    return t.contiguous().view(torch.uint8).numpy()
+
+
+def decode_fp8_case(tag, num_batch, kv_lens, hkv, hq, seed, layout):
+    fn = extract(REF / "tests/test_attention_decode_qpertoken_perhead_kvpertensor_fp8.py",
+                 "ref_attn_with_paged_kvcache_func")
+    d = oa.make_decode_fp8_inputs(num_batch, 1, kv_lens, hkv, hq, seed=seed, layout=layout)
+    lens = d["kv_lens_total"]
+    nblocks = (lens + 63) // 64
+    seqlenq = torch.ones(num_batch, dtype=torch.int32)
+    kdummy = torch.empty(num_batch, hkv, 128)
+    gt = fn(d["q"], kdummy, kdummy, d["kvcache"], d["block_ids"], nblocks, seqlenq, None,
+            lens - 1, d["q_scale"], d["k_scale"], d["v_scale"])
+    np.savez_compressed(
+        OUT / f"decode_fp8_{tag}.npz", q=u8(d["q"]), q_scale=d["q_scale"].numpy(),
+        kvcache=u8(d["kvcache"].contiguous()), k_scale=d["k_scale"].numpy(),
+        v_scale=d["v_scale"].numpy(), block_ids=d["block_ids"].numpy(), kv_lens_total=lens.numpy(),
+        out=gt.float().numpy(), meta=np.array([num_batch, 1, hkv, hq, 128, 64]),
+        layout=np.array([0 if layout == "NHD" else 1]))
+    print("wrote", tag, gt.shape)
+
+
+def decode_bf16_c1():
+    """BASELINE config 0: test_attention_decode_bf16 bs=2 h=4 d=64 seq=128 on the torch CPU path."""
+    fn = extract(REF / "tests/test_attention_decode_bf16.py", "ref_attn_with_paged_kvcache_func")
+    torch.manual_seed(41)
+    B, Hkv, Hq, D, bs = 2, 1, 4, 64, 64
+    lens = torch.randint(1, 128, (B,), dtype=torch.int32) + 1
+    nblocks = (lens + bs - 1) // bs
+    q = (torch.randn(B, Hq, D) / math.sqrt(D)).to(torch.bfloat16)
+    kvcache = (torch.randn(8, 2, bs, Hkv, D) / math.sqrt(D)).to(torch.bfloat16)
+    block_ids = torch.zeros(B, int(nblocks.max()), dtype=torch.int32)
+    perm = torch.randperm(8)
+    cu = 0
+    for i in range(B):
+        block_ids[i, : nblocks[i]] = perm[cu:cu + int(nblocks[i])]
+        cu += int(nblocks[i])
+    seqlenq = torch.ones(B, dtype=torch.int32)
+    kd = torch.empty(B, Hkv, D)
+    gt = fn(q, kd, kd, kvcache, block_ids, nblocks, seqlenq, None, lens - 1)
+    np.savez_compressed(OUT / "decode_bf16_c1.npz", q=q.float().numpy(),
+                        kvcache=kvcache.float().numpy(), block_ids=block_ids.numpy(),
+                        kv_lens_total=lens.numpy(), out=gt.float().numpy())
+    print("wrote decode_bf16_c1", gt.shape)
+
+
+def taskmap_cases():
+    assert otm.ref_lib() is not None, "run `make -C oracle ref` first"
+    rng = np.random.default_rng(7)
+    cases = []
+    cfgs = [(1, 1, 1, 128, 148, 1024, 4096), (16, 4, 2, 128, 148, 1024, 4096),
+            (200, 4, 4, 128, 148, 1024, 1024), (64, 8, 1, 128, 148, 64, 8193),
+            (200, 1, 3, 64, 592, 1024, 4096), (33, 8, 4, 128, 148, 512, 300),
+            (7, 2, 4, 128, 148, 64, 40000), (500, 8, 2, 64, 296, 2048, 700)]
+    for i, (B, H, sq, tilen, ctas, mpl, mx) in enumerate(cfgs):
+        lens = (rng.integers(1, mx, size=B) + sq).astype(np.int32)
+        ref = otm.assign_ref(lens, ctas, H, sq, tilen, True, mpl)
+        ref[1:1 + (ref[0, 0] * ctas), 9:] = 0
+        cases.append(dict(lens=lens, cfg=np.array([B, H, sq, tilen, ctas, mpl]), out=ref))
+    np.savez_compressed(OUT / "taskmap_ref.npz",
+                        **{f"{k}_{i}": v for i, c in enumerate(cases) for k, v in c.items()},
+                        n=np.array([len(cases)]))
+    print("wrote taskmap_ref", len(cases))
+
+
+if __name__ == "__main__":
+    decode_fp8_case("b2_nhd", 2, [100, 129], 1, 8, 41, "NHD")
+    decode_fp8_case("b5_hnd", 5, [1, 64, 65, 300, 515], 2, 16, 10086, "HND")
+    decode_bf16_c1()
+    taskmap_cases()
