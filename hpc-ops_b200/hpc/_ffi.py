@@ -41,6 +41,10 @@ lib.hpc_attention_decode_fp8_async.argtypes = (
     [c_ptr] * 13 + [c_int] * 18 + [c_i64] * 6 + [c_ptr]
 )
 
+for _n in ("hpc_attention_decode_fp8_partial_async", "hpc_attention_decode_fp8_combine_async"):
+    getattr(lib, _n).restype = c_int
+    getattr(lib, _n).argtypes = lib.hpc_attention_decode_fp8_async.argtypes
+
 lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]

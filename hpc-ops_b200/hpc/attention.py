@@ -49,6 +49,19 @@ def _attention_decode_fp8_impl(
     q, kcache, vcache, block_ids, num_seq_kvcache, qscale, kscale, vscale, mtp, new_kv_included,
     quant_type, use_splitk, task_map, split_flag, output,
 ):
+    y, args, _keep = _decode_fp8_prepare(
+        q, kcache, vcache, block_ids, num_seq_kvcache, qscale, kscale, vscale, mtp,
+        new_kv_included, quant_type, use_splitk, task_map, split_flag, output)
+    _check_rc(_lib.hpc_attention_decode_fp8_async(*args), "attention_decode_fp8")
+    return y
+
+
+def _decode_fp8_prepare(
+    q, kcache, vcache, block_ids, num_seq_kvcache, qscale, kscale, vscale, mtp, new_kv_included,
+    quant_type, use_splitk, task_map, split_flag, output,
+):
+    """Validate, allocate scratch and marshal the C-ABI argument tuple.
+    Returns (y, args, keepalive)."""
     # validation mirrors reference src/attention/entry.cc:580-616
     _require(q.is_cuda, "q tensor must be cuda")
     _require(kcache.is_cuda and vcache.is_cuda, "kv cache tensors must be cuda")
@@ -104,7 +117,7 @@ def _attention_decode_fp8_impl(
     split_out = torch.empty((num_batch, splitk, num_seq_q, num_head_q, num_dim_v),
                             dtype=torch.float32, device=q.device)
 
-    rc = _lib.hpc_attention_decode_fp8_async(
+    args = (
         _ptr(y), _ptr(lse), _ptr(split_out), _ptr(task_map), _ptr(q), _ptr(kcache), _ptr(vcache),
         _ptr(block_ids), _ptr(num_seq_kvcache), _ptr(qscale), _ptr(kscale), _ptr(vscale),
         _ptr(split_flag),
@@ -116,8 +129,7 @@ def _attention_decode_fp8_impl(
         vcache.stride(0), vcache.stride(1), vcache.stride(2),
         _stream_of(q),
     )
-    _check_rc(rc, "attention_decode_fp8")
-    return y
+    return y, args, (lse, split_out, task_map)
 
 
 def _assign_task_cpu(num_seq_kvcache, num_head_kv, num_seq_q, new_kv_included, min_process_len,

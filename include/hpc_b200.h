@@ -79,6 +79,32 @@ int hpc_attention_decode_fp8_async(
     int64_t kcache_token_stride, int64_t kcache_head_stride, int64_t vcache_block_stride,
     int64_t vcache_token_stride, int64_t vcache_head_stride, cudaStream_t stream);
 
+/* The two stages of hpc_attention_decode_fp8_async on their own, same argument list: the split-k
+ * attention kernel (writes lse / split_out) and the LSE combine (reads them, writes y). The
+ * reference launches them back to back inside one launcher
+ * (src/attention/decode/sm90/dynamic/...dynamic.cu:44-195); they are exposed separately so the
+ * dominant kernel can be timed alone. */
+int hpc_attention_decode_fp8_partial_async(
+    void* y_ptr, void* lse_ptr, void* split_out_ptr, const int* task_map_ptr, const void* q_ptr,
+    void* kcache_ptr, void* vcache_ptr, const int* block_ids_ptr, const int* num_seq_kvcache_ptr,
+    const float* qscale_ptr, const float* kscale_ptr, const float* vscale_ptr, int* split_flag_ptr,
+    int new_kv_included, int splitk, int splitk_min_len, int consumers, int quant_type,
+    int num_batch, int num_seq_q, int num_head_q, int num_head_k, int num_head_v, int num_dim_qk,
+    int num_dim_v, int num_kvcache_blocks, int block_size, int num_seq_max_blocks,
+    int qscale_pad_stride, int ldY, int ldQ, int64_t kcache_block_stride,
+    int64_t kcache_token_stride, int64_t kcache_head_stride, int64_t vcache_block_stride,
+    int64_t vcache_token_stride, int64_t vcache_head_stride, cudaStream_t stream);
+int hpc_attention_decode_fp8_combine_async(
+    void* y_ptr, void* lse_ptr, void* split_out_ptr, const int* task_map_ptr, const void* q_ptr,
+    void* kcache_ptr, void* vcache_ptr, const int* block_ids_ptr, const int* num_seq_kvcache_ptr,
+    const float* qscale_ptr, const float* kscale_ptr, const float* vscale_ptr, int* split_flag_ptr,
+    int new_kv_included, int splitk, int splitk_min_len, int consumers, int quant_type,
+    int num_batch, int num_seq_q, int num_head_q, int num_head_k, int num_head_v, int num_dim_qk,
+    int num_dim_v, int num_kvcache_blocks, int block_size, int num_seq_max_blocks,
+    int qscale_pad_stride, int ldY, int ldQ, int64_t kcache_block_stride,
+    int64_t kcache_token_stride, int64_t kcache_head_stride, int64_t vcache_block_stride,
+    int64_t vcache_token_stride, int64_t vcache_head_stride, cudaStream_t stream);
+
 /* ---- bring-up self test: one CTA, nk tcgen05.mma (kind::f8f6f4) with caller-supplied smem
  * images and descriptor fields; D[128, ncols] fp32 is copied out of TMEM. Used by tests to pin
  * the UMMA descriptor conventions the kernels rely on. */
