@@ -17,6 +17,8 @@
 //   :523-602 (final), :638-660 (lse)
 // and the launcher contract of
 //   src/attention/decode/decode.h:28-37 (attention_decode_fp8_async).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host_utils.h"
 
@@ -27,7 +29,6 @@ constexpr int kTileN = 128;  // keys per tile == UMMA M
 constexpr int kPage = 64;    // paged block size (tokens)
 constexpr int kD = 128;      // head dim
 constexpr int kSlotBytes = kTileN * kD;  // 16 KB (fp8)
-constexpr int kNumSlots = 12;
 constexpr int kThreads = 192;
 constexpr int kTaskStride = 12;
 constexpr int kSoftmaxBar = 1;
@@ -77,21 +78,33 @@ __device__ __forceinline__ bool load_task(const int* row, Task& t) {
   return true;
 }
 
+constexpr int kNumStages = 6;                 // (K tile + V tile) stages of 32 KB
+constexpr int kStageBytes = 2 * kSlotBytes;
+
 template <int NQ>
 struct Smem {
-  static constexpr int kQBytes = NQ * kD;            // one Q buffer (SW128 rows of 128 B)
   static constexpr int kPPlanes = NQ / 16;
   static constexpr int kPBytes = kPPlanes * kTileN * 16;  // one P buffer
-  static constexpr int kOffSlots = 0;
-  static constexpr int kOffQ = kNumSlots * kSlotBytes;
+  static constexpr int kOffStages = 0;
+  static constexpr int kOffQ = kNumStages * kStageBytes;
   static constexpr int kOffP = kOffQ + 2 * 4096;  // Q buffers padded to 4 KB (1024-B aligned)
   static constexpr int kOffMax = kOffP + 2 * kPBytes;
   static constexpr int kOffBar = kOffMax + 2 * 4 * 32 * 4;
-  static constexpr int kNumBars = 2 * kNumSlots + 16;
+  static constexpr int kNumBars = 3 * kNumStages + 10;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmem + 16;
 };
 
+// Synchronisation protocol (all mbarriers, phase = use count parity):
+//   k_full[st], v_full[st]  producer TMA bytes landed          -> MMA thread
+//   stage_empty[st]         tcgen05.commit after PV of the tile -> producer (K and V slots free)
+//   q_full/q_empty[qb]      Q rows of a task                    (producer <-> MMA thread)
+//   s_full[buf]             commit after QK                     -> softmax warps
+//   p_full[buf]             128 softmax threads wrote P^T       -> MMA thread
+//   o_full[buf]             commit after PV                     -> softmax warps
+// No "empty" barriers are needed for S, P and O: the MMA thread issues QK(n) only after it has
+// waited p_full(n-2) (softmax threads arrive on it after their tcgen05.ld of S(n-2) and O(n-3)),
+// and a softmax thread writes P(n) only after it has consumed O(n-2), i.e. PV(n-2) completed.
 template <int NQ, int RL>
 __global__ void __launch_bounds__(kThreads, 1)
     decode_attn_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -100,24 +113,21 @@ __global__ void __launch_bounds__(kThreads, 1)
   using L = Smem<NQ>;
   extern __shared__ __align__(1024) uint8_t smem[];
 
-  uint8_t* slots = smem + L::kOffSlots;
+  uint8_t* stages = smem + L::kOffStages;
   uint8_t* q_smem = smem + L::kOffQ;
   uint8_t* p_smem = smem + L::kOffP;
   float* smax = reinterpret_cast<float*>(smem + L::kOffMax);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
-  uint64_t* slot_full = bars;
-  uint64_t* slot_empty = bars + kNumSlots;
-  uint64_t* q_full = bars + 2 * kNumSlots;
+  uint64_t* k_full = bars;
+  uint64_t* v_full = bars + kNumStages;
+  uint64_t* stage_empty = bars + 2 * kNumStages;
+  uint64_t* q_full = bars + 3 * kNumStages;
   uint64_t* q_empty = q_full + 2;
   uint64_t* s_full = q_full + 4;
-  uint64_t* s_empty = q_full + 6;
-  uint64_t* p_full = q_full + 8;
-  uint64_t* p_empty = q_full + 10;
-  uint64_t* o_full = q_full + 12;
-  uint64_t* o_empty = q_full + 14;
-  static_assert(L::kNumBars >= 2 * kNumSlots + 16, "barrier count");
+  uint64_t* p_full = q_full + 6;
+  uint64_t* o_full = q_full + 8;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -136,19 +146,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_k);
     prefetch_tensormap(&tmap_v);
-    for (int i = 0; i < kNumSlots; i++) {
-      mbar_init(&slot_full[i], 1);
-      mbar_init(&slot_empty[i], 1);
+    for (int i = 0; i < kNumStages; i++) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&stage_empty[i], 1);
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128);
-      mbar_init(&p_empty[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
     }
     fence_barrier_init();
   }
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // =========================== TMA producer ===========================================
     const uint64_t pol_stream = make_policy_evict_first();
-    uint32_t j = 0;      // kv slot counter (K of tile n -> 2n, V -> 2n+1)
+    uint32_t n = 0;      // global tile counter of this CTA
     uint32_t qcnt = 0;   // task counter for the Q double buffer
     Task t;
     for (const int* row = bin; load_task(row, t); row += kTaskStride) {
@@ -189,108 +197,91 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int vc2 = p.v_head_first ? 0 : t.ihead_kv;
       for (int g0 = 0; g0 < ntiles; g0 += 16) {
         int bi = g0 * 2 + lane;
-        bi = bi < nblk ? bi : nblk - 1;
+        bi = bi < nblk ? bi : nblk - 1;  // a missing 2nd page of the last tile re-reads the 1st
         const int my_id = __ldg(ids + bi);
         const int gt = (ntiles - g0) < 16 ? (ntiles - g0) : 16;
         for (int tt = 0; tt < gt; tt++) {
           const int id0 = __shfl_sync(0xffffffffu, my_id, 2 * tt);
           const int id1 = __shfl_sync(0xffffffffu, my_id, 2 * tt + 1);
           if (lane == 0) {
-            {
-              const uint32_t s = j % kNumSlots;
-              mbar_wait(&slot_empty[s], ((j / kNumSlots) & 1) ^ 1);
-              mbar_arrive_expect_tx(&slot_full[s], kSlotBytes);
-              uint8_t* dst = slots + s * kSlotBytes;
-              tma_load_4d_hint(dst, &tmap_k, &slot_full[s], 0, kc1, kc2, id0, pol_stream);
-              tma_load_4d_hint(dst + kSlotBytes / 2, &tmap_k, &slot_full[s], 0, kc1, kc2, id1,
-                               pol_stream);
-            }
-            {
-              const uint32_t s = (j + 1) % kNumSlots;
-              mbar_wait(&slot_empty[s], (((j + 1) / kNumSlots) & 1) ^ 1);
-              mbar_arrive_expect_tx(&slot_full[s], kSlotBytes);
-              uint8_t* dst = slots + s * kSlotBytes;
-              tma_load_4d_hint(dst, &tmap_v, &slot_full[s], 0, vc1, vc2, id0, pol_stream);
-              tma_load_4d_hint(dst + kSlotBytes / 2, &tmap_v, &slot_full[s], 0, vc1, vc2, id1,
-                               pol_stream);
-            }
+            const uint32_t st = n % kNumStages;
+            mbar_wait(&stage_empty[st], ((n / kNumStages) & 1) ^ 1);
+            uint8_t* dst = stages + st * kStageBytes;
+            mbar_arrive_expect_tx(&k_full[st], kSlotBytes);
+            tma_load_4d_hint(dst, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_stream);
+            tma_load_4d_hint(dst + kSlotBytes / 2, &tmap_k, &k_full[st], 0, kc1, kc2, id1,
+                             pol_stream);
+            mbar_arrive_expect_tx(&v_full[st], kSlotBytes);
+            tma_load_4d_hint(dst + kSlotBytes, &tmap_v, &v_full[st], 0, vc1, vc2, id0,
+                             pol_stream);
+            tma_load_4d_hint(dst + kSlotBytes + kSlotBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2,
+                             id1, pol_stream);
           }
-          j += 2;
+          n++;
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== tcgen05 issuer ==========================================
-    constexpr uint32_t idesc_qk = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 1, 1);
-    const uint32_t slots_addr = smem_u32(slots);
-    const uint32_t q_addr = smem_u32(q_smem);
-    const uint32_t p_addr = smem_u32(p_smem);
+    // =========================== tcgen05 issuer (one thread) ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 1, 1);
+      // Descriptor templates; per tile only the 14-bit start-address field (units of 16 B) moves.
+      //  K tile / Q rows : K-major, 128B swizzle, 8-row groups 1024 B apart, K advances 32 B / MMA
+      //  V tile          : MN-major (d contiguous, exactly as stored), 128B swizzle, 8-key groups
+      //                    1024 B apart, one MMA consumes 32 keys = 4096 B
+      //  P^T             : MN-major, no swizzle, [key][16 queries] planes: 8-key core matrices
+      //                    128 B apart (LBO), second plane kTileN*16 B away (SBO); 512 B / MMA
+      const uint64_t kdesc0 = make_smem_desc(smem_u32(stages), 16, 1024, kLayoutSW128);
+      const uint64_t vdesc0 = make_smem_desc(smem_u32(stages) + kSlotBytes, 16, 1024, kLayoutSW128);
+      const uint64_t qdesc0 = make_smem_desc(smem_u32(q_smem), 16, 1024, kLayoutSW128);
+      const uint64_t pdesc0 = make_smem_desc(smem_u32(p_smem), 128, kTileN * 16, kLayoutNone);
 
-    auto issue_pv = [&](uint32_t m) {
-      const uint32_t jv = 2 * m + 1;
-      const uint32_t s = jv % kNumSlots;
-      const uint32_t buf = m & 1;
-      const uint32_t ph = (m >> 1) & 1;
-      mbar_wait(&p_full[buf], ph);
-      mbar_wait(&slot_full[s], (jv / kNumSlots) & 1);
-      mbar_wait(&o_empty[buf], ph ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t va = slots_addr + s * kSlotBytes;
-        const uint32_t pa = p_addr + buf * L::kPBytes;
+      auto issue_pv = [&](uint32_t m) {
+        const uint32_t st = m % kNumStages;
+        const uint32_t buf = m & 1;
+        mbar_wait(&p_full[buf], (m >> 1) & 1);
+        mbar_wait(&v_full[st], (m / kNumStages) & 1);
+        tc_fence_after();
+        const uint64_t ad = vdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
+        const uint64_t bd = pdesc0 + static_cast<uint64_t>(buf * (L::kPBytes >> 4));
+        const uint32_t d = tmem_base + 2 * NQ + buf * NQ;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          // A = V tile as stored ([key][d], d contiguous): MN-major, 128B swizzle,
-          //     8-key groups 1024 B apart; one MMA consumes 32 keys = 4096 B.
-          const uint64_t ad = make_smem_desc(va + k * 4096, 16, 1024, kLayoutSW128);
-          // B = P^T ([key][16 queries] planes): MN-major, no swizzle; 8-key core matrices are
-          //     128 B apart (LBO), the second 16-query plane is kTileN*16 B away (SBO).
-          const uint64_t bd = make_smem_desc(pa + k * 512, 128, kTileN * 16, kLayoutNone);
-          umma_f8(tmem_base + 2 * NQ + buf * NQ, ad, bd, idesc_pv, k > 0);
+          umma_f8(d, ad + k * (4096 >> 4), bd + k * (512 >> 4), idesc_pv, k > 0);
         }
-        umma_commit(&slot_empty[s]);
-        umma_commit(&p_empty[buf]);
+        umma_commit(&stage_empty[st]);
         umma_commit(&o_full[buf]);
-      }
-      __syncwarp();
-    };
+      };
 
-    uint32_t n = 0;
-    uint32_t qcnt = 0;
-    Task t;
-    for (const int* row = bin; load_task(row, t); row += kTaskStride) {
-      const int qb = qcnt & 1;
-      mbar_wait(&q_full[qb], (qcnt >> 1) & 1);
-      const int ntiles = t.num_tile_kv;
-      for (int tt = 0; tt < ntiles; tt++) {
-        const uint32_t jk = 2 * n;
-        const uint32_t s = jk % kNumSlots;
-        const uint32_t buf = n & 1;
-        mbar_wait(&slot_full[s], (jk / kNumSlots) & 1);
-        mbar_wait(&s_empty[buf], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t ka = slots_addr + s * kSlotBytes;
-          const uint32_t qa = q_addr + qb * 4096;
+      uint32_t n = 0;
+      uint32_t qcnt = 0;
+      Task t;
+      for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+        const int qb = qcnt & 1;
+        mbar_wait(&q_full[qb], (qcnt >> 1) & 1);
+        const uint64_t bd = qdesc0 + static_cast<uint64_t>(qb * (4096 >> 4));
+        const int ntiles = t.num_tile_kv;
+        for (int tt = 0; tt < ntiles; tt++) {
+          const uint32_t st = n % kNumStages;
+          const uint32_t buf = n & 1;
+          mbar_wait(&k_full[st], (n / kNumStages) & 1);
+          tc_fence_after();
+          const uint64_t ad = kdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
+          const uint32_t d = tmem_base + buf * NQ;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart; K advances 32 B.
-            const uint64_t ad = make_smem_desc(ka + k * 32, 16, 1024, kLayoutSW128);
-            const uint64_t bd = make_smem_desc(qa + k * 32, 16, 1024, kLayoutSW128);
-            umma_f8(tmem_base + buf * NQ, ad, bd, idesc_qk, k > 0);
+            umma_f8(d, ad + k * (32 >> 4), bd + k * (32 >> 4), idesc_qk, k > 0);
           }
-          umma_commit(&slot_empty[s]);
           umma_commit(&s_full[buf]);
           if (tt == ntiles - 1) umma_commit(&q_empty[qb]);
+          if (n > 0) issue_pv(n - 1);
+          n++;
         }
-        __syncwarp();
-        if (n > 0) issue_pv(n - 1);
-        n++;
+        qcnt++;
       }
-      qcnt++;
+      if (n > 0) issue_pv(n - 1);
     }
-    if (n > 0) issue_pv(n - 1);
   } else {
     // =========================== softmax / epilogue warps =================================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
@@ -337,8 +328,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           tmem_ld_x32(lane_addr + 2 * NQ + buf * NQ, o);
         }
         tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive(&o_empty[buf]);
 #pragma unroll
         for (int r = 0; r < RL; r++) {
           acc[r] = acc[r] * alpha_pend[r] + __uint_as_float(o[r]);
@@ -357,8 +346,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           tmem_ld_x32(lane_addr + buf * NQ, sraw);
         }
         tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive(&s_empty[buf]);
 
         const int key = tt * kTileN + row_in_tile;
         const int lim_min = lim_len < lim_causal ? lim_len : lim_causal;
@@ -397,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           x[r] = a;
         }
         // ---- P^T row of this key -> smem (e4m3), 16 queries per plane ----
-        mbar_wait(&p_empty[buf], ph ^ 1);
+        // (P buffer `buf` is free: this thread consumed O(n-2) last iteration => PV(n-2) done)
         {
           uint8_t* pb = p_smem + buf * L::kPBytes + row_in_tile * 16;
 #pragma unroll
@@ -417,6 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         fence_proxy_async_smem();
+        tc_fence_before();  // orders this thread's tcgen05.ld of S(n) and O(n-2) before the arrive
         mbar_arrive(&p_full[buf]);
 
         if (tt > 0) consume_o(n - 1);
@@ -653,7 +641,19 @@ static int decode_fp8_impl(
     dims[3] = static_cast<uint64_t>(num_kvcache_blocks);
     strides[2] = static_cast<uint64_t>(blk_stride);
     box[3] = 1;
-    return encode_tmap_u8(tm, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    // L2 promotion must not exceed the contiguous run of one head's row: with token rows of
+    // 128 B strided by Hkv*128 B (NHD) a 256 B promotion drags in the neighbouring head's row,
+    // which is consumed by another CTA much later (measured: +49 % DRAM reads, profiles/).
+    CUtensorMapL2promotion promo = (tok_stride == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                       : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* e = getenv("HPC_B200_KV_PROMO")) {  // tuning knob: 0 none, 1 64B, 2 128B, 3 256B
+      const int v = atoi(e);
+      promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                     : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                       : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
+    return encode_tmap_u8(tm, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, promo);
   };
   int k_head_first = 1, v_head_first = 1;
   {

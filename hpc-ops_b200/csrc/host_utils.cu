@@ -49,7 +49,7 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, const void* base,
                 int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                CUtensorMapSwizzle swizzle) {
+                CUtensorMapSwizzle swizzle, CUtensorMapL2promotion promo) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -67,7 +67,7 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, con
   }
   (void)elem_bytes;
   CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
-                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error(
@@ -86,9 +86,10 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, con
 }
 
 int encode_tmap_u8(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                   CUtensorMapL2promotion promo) {
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, rank, dims, strides_bytes, box,
-                     swizzle);
+                     swizzle, promo);
 }
 
 }  // namespace b200

@@ -37,10 +37,12 @@ int sm_count();
 // Encode a tiled TMA descriptor (uint8 elements). dims/strides innermost-first; strides in bytes for
 // dims 1..rank-1. Returns 0 on success.
 int encode_tmap_u8(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                   CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 // Same for 2-byte and 4-byte element types.
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, const void* base,
                 int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                CUtensorMapSwizzle swizzle);
+                CUtensorMapSwizzle swizzle,
+                CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 
 }  // namespace b200
