@@ -45,6 +45,23 @@ for _n in ("hpc_attention_decode_fp8_partial_async", "hpc_attention_decode_fp8_c
     getattr(lib, _n).restype = c_int
     getattr(lib, _n).argtypes = lib.hpc_attention_decode_fp8_async.argtypes
 
+lib.hpc_group_gemm_blockwise_fp8_async.restype = c_int
+lib.hpc_group_gemm_blockwise_fp8_async.argtypes = [c_ptr] * 11 + [c_int] * 10 + [c_ptr]
+lib.hpc_group_gemm_fp8_async.restype = c_int
+lib.hpc_group_gemm_fp8_async.argtypes = [c_ptr] * 10 + [c_int] * 8 + [c_ptr]
+lib.hpc_reformat_x_scale_async.restype = c_int
+lib.hpc_reformat_x_scale_async.argtypes = [c_ptr] * 4 + [c_int] * 4 + [c_ptr]
+lib.hpc_count_and_gather_async.restype = c_int
+lib.hpc_count_and_gather_async.argtypes = [c_ptr] * 15 + [c_int] * 7 + [c_ptr]
+lib.hpc_blockwise_count_and_gather_async.restype = c_int
+lib.hpc_blockwise_count_and_gather_async.argtypes = [c_ptr] * 17 + [c_int] * 9 + [c_ptr]
+lib.hpc_reduce_async.restype = c_int
+lib.hpc_reduce_async.argtypes = [c_ptr] * 5 + [c_int] * 5 + [c_ptr]
+lib.hpc_fuse_moe_async.restype = c_int
+lib.hpc_fuse_moe_async.argtypes = [c_ptr] * 23 + [c_int] * 10 + [c_ptr]
+lib.hpc_fuse_moe_blockwise_async.restype = c_int
+lib.hpc_fuse_moe_blockwise_async.argtypes = [c_ptr] * 25 + [c_int] * 12 + [c_ptr]
+
 lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]

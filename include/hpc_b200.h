@@ -105,6 +105,82 @@ int hpc_attention_decode_fp8_combine_async(
     int64_t kcache_token_stride, int64_t kcache_head_stride, int64_t vcache_block_stride,
     int64_t vcache_token_stride, int64_t vcache_head_stride, cudaStream_t stream);
 
+/* ---- grouped FP8 GEMM -------------------------------------------------------------------------
+ * replaces reference src/group_gemm/group_gemm.h:12-29. X [m, k] e4m3 with the rows of group g at
+ * cu_seqlens[g] .. +seqlens[g]; W [num_group, n, k] e4m3; Y [m, n] bf16.
+ *   blockwise : xscale f32 [k/128, m_pad] (column of row i of group g = sum_{g'<g} pad(seqlens[g'],
+ *               tile(num_seq_per_group_avg)) + i), wscale f32 [num_group, n/128, num_block_k_pad4]
+ *   per-tensor: y_scale f32 [num_group]
+ * tmas / tiles / cu_tiles / task_map / num_waves / update_tma / use_pdl are accepted and ignored
+ * (the sm_100a kernel derives its schedule on the device).
+ */
+int hpc_group_gemm_blockwise_fp8_async(
+    void* y_ptr, const void* x_ptr, const void* w_ptr, const void* seqlens_ptr,
+    const void* cu_seqlens_ptr, const void* xscale_ptr, const void* wscale_ptr, void* tmas_ptr,
+    void* tiles_ptr, void* cu_tiles_ptr, void* task_map_ptr, int num_waves, int num_group, int m,
+    int n, int k, int m_pad, int num_block_k_pad4, int num_seq_per_group_avg, int update_tma,
+    int use_pdl, cudaStream_t stream);
+int hpc_group_gemm_fp8_async(void* y_ptr, const void* x_ptr, const void* w_ptr,
+                             const void* seqlens_ptr, const void* cu_seqlens_ptr,
+                             const void* y_scale, void* tmas_ptr, void* tiles_ptr,
+                             void* cu_tiles_ptr, void* task_map_ptr, int num_waves, int num_group,
+                             int m, int n, int k, int num_seq_per_group_avg, int update_tma,
+                             int use_pdl, cudaStream_t stream);
+/* replaces reference src/group_gemm/group_gemm.h:31-33 (row-major [m, n] scales -> transposed,
+ * tile-padded [n, m] layout the blockwise GEMM reads) */
+int hpc_reformat_x_scale_async(void* output_ptr, const void* xscale_ptr, const void* seqlens_ptr,
+                               const void* cu_seqlens_ptr, int num_group, int m, int n, int tilem,
+                               cudaStream_t stream);
+
+/* ---- FusedMoE -----------------------------------------------------------------------------------
+ * replace reference src/fuse_moe/fuse_moe.h:15-62, argument for argument (bool -> int).
+ * `intermediate_size` is gate_up_weight.size(1) (= 2*I) as in the reference entries.
+ * In this build gate_up_output_ptr may be NULL: SiLU*mul + FP8 re-quant is the epilogue of the
+ * Gate-Up GEMM and the bf16 Gate-Up matrix is never materialised.
+ */
+int hpc_count_and_gather_async(
+    void* gate_up_input_ptr, void* gate_up_output_ptr, void* down_input_ptr, void* down_output_ptr,
+    const void* x_ptr, const void* topk_ids_ptr, void* topk_pos_ptr, void* seqlens_ptr,
+    void* cu_seqlens_ptr, void* gate_up_tmas_ptr, void* down_tmas_ptr, void* tiles_ptr,
+    void* cu_tiles_ptr, void* gateup_task_map_ptr, void* down_task_map_ptr, int num_seq,
+    int hidden_size, int intermediate_size, int num_topk, int num_expert, int eprank,
+    int num_seq_per_group_avg, cudaStream_t stream);
+int hpc_blockwise_count_and_gather_async(
+    const void* input_ptr, const void* input_scale_ptr, void* gate_up_input_ptr,
+    void* gate_up_output_ptr, void* gate_up_input_scale_ptr, void* down_input_ptr,
+    void* down_output_ptr, const void* topk_ids_ptr, void* topk_pos_ptr,
+    void* num_tokens_per_group_ptr, void* cu_num_tokens_per_group_ptr, void* gate_up_tmas_ptr,
+    void* down_tmas_ptr, void* tiles_ptr, void* cu_tiles_ptr, void* gateup_task_map_ptr,
+    void* down_task_map_ptr, int num_tokens, int num_padded_tokens, int hidden_size,
+    int intermediate_size, int num_topk, int num_expert_local, int eprank,
+    int num_tokens_per_group_avg, int use_pdl, cudaStream_t stream);
+int hpc_reduce_async(void* y_ptr, const void* x_ptr, const void* topk_pos_ptr,
+                     const void* topk_scale_ptr, const void* shared_output_ptr, int total_num_seq,
+                     int num_seq, int hidden_size, int num_topk, int use_pdl, cudaStream_t stream);
+int hpc_fuse_moe_async(
+    void* output_ptr, const void* input_ptr, void* gate_up_input_ptr, void* gate_up_output_ptr,
+    const void* gate_up_weight_ptr, const void* gate_up_scale_ptr, void* gate_up_tmas_ptr,
+    const void* act_and_mul_scale_ptr, void* down_input_ptr, void* down_output_ptr,
+    const void* down_weight_ptr, const void* down_scale_ptr, void* down_tmas_ptr,
+    const void* topk_ids_ptr, const void* topk_scale_ptr, void* topk_pos_ptr, void* seqlens_ptr,
+    void* cu_seqlens_ptr, void* tiles_ptr, void* cu_tiles_ptr, const void* shared_output_ptr,
+    void* gateup_task_map_ptr, void* down_task_map_ptr, int num_gateup_waves, int num_down_waves,
+    int num_seq, int hidden_size, int intermediate_size, int num_topk, int num_expert_total,
+    int num_expert_local, int rank_ep, int use_bf16_mul, cudaStream_t stream);
+int hpc_fuse_moe_blockwise_async(
+    void* output_ptr, const void* input_ptr, const void* input_scale_ptr, void* gate_up_input_ptr,
+    void* gate_up_input_scale_ptr, void* gate_up_output_ptr, const void* gate_up_weight_ptr,
+    const void* gate_up_weight_scale_ptr, void* gate_up_tmas_ptr, void* down_input_ptr,
+    void* down_input_scale_ptr, void* down_output_ptr, const void* down_weight_ptr,
+    const void* down_weight_scale_ptr, void* down_tmas_ptr, const void* topk_ids_ptr,
+    const void* topk_scale_ptr, void* topk_pos_ptr, void* num_tokens_per_group_ptr,
+    void* cu_num_tokens_per_group_ptr, void* tiles_ptr, void* cu_tiles_ptr,
+    const void* shared_output_ptr, void* gateup_task_map_ptr, void* down_task_map_ptr,
+    int num_gateup_waves, int num_down_waves, int num_tokens, int num_padded_tokens,
+    int hidden_size, int intermediate_size, int num_topk, int num_expert_total,
+    int num_expert_local, int gate_up_weight_scale_lastdim_pad4, int down_weight_scale_lastdim_pad4,
+    int rank_ep, cudaStream_t stream);
+
 /* ---- bring-up self test: one CTA, nk tcgen05.mma (kind::f8f6f4) with caller-supplied smem
  * images and descriptor fields; D[128, ncols] fp32 is copied out of TMEM. Used by tests to pin
  * the UMMA descriptor conventions the kernels rely on. */

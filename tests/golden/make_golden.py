@@ -105,7 +105,82 @@ def taskmap_cases():
     print("wrote taskmap_ref", len(cases))
 
 
+class _TorchCPU:
+    """`torch` stand-in for exec'ing reference test functions that hard-code device="cuda"."""
+
+    def __getattr__(self, name):
+        attr = getattr(torch, name)
+        if callable(attr) and not isinstance(attr, type):
+            def wrapped(*a, **k):
+                if k.get("device", None) == "cuda":
+                    k["device"] = "cpu"
+                return attr(*a, **k)
+            return wrapped
+        return attr
+
+
+def extract_many(path: Path, names):
+    src = path.read_text()
+    tree = ast.parse(src)
+    ns = {"torch": _TorchCPU(), "math": math, "F": torch.nn.functional, "Tuple": tuple}
+    from typing import Tuple
+    ns["Tuple"] = Tuple
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.get_source_segment(src, node), str(path), "exec"), ns)
+    return ns
+
+
+def moe_blockwise_case(tag, T, K, H, I, E_total, size_ep, rank_ep, shared, seed):
+    from oracle import moe as om
+    ns = extract_many(REF / "tests/test_fuse_moe_blockwise.py",
+                      {"naive_gather_expert_inputs", "naive_group_gemm",
+                       "naive_act_mul_and_blockwise_quant", "naive_reduce",
+                       "naive_fuse_moe_blockwise_fp8"})
+    d = om.make_moe_blockwise_inputs(T, K, H, I, E_total, size_ep, shared, seed)
+    gt = ns["naive_fuse_moe_blockwise_fp8"](
+        d["x"], d["x_scale"], d["gate_up_weight"], d["gate_up_weight_scale"], d["down_weight"],
+        d["down_weight_scale"], d["topk_ids"], d["topk_scale"], rank_ep, E_total,
+        d["shared_output"])
+    g = ns["naive_gather_expert_inputs"](d["x"], d["x_scale"], d["topk_ids"], E_total // size_ep, rank_ep)
+    np.savez_compressed(
+        OUT / f"moe_blockwise_{tag}.npz", x=u8(d["x"]), x_scale=d["x_scale"].numpy(),
+        guw=u8(d["gate_up_weight"]), guws=d["gate_up_weight_scale"].numpy(),
+        dw=u8(d["down_weight"]), dws=d["down_weight_scale"].numpy(),
+        topk_ids=d["topk_ids"].numpy(), topk_scale=d["topk_scale"].numpy(),
+        shared=(d["shared_output"].float().numpy() if shared else np.zeros(0, np.float32)),
+        out=gt.float().numpy(), topk_pos=g[2].numpy(), counts=g[3].numpy(), cu=g[4].numpy(),
+        meta=np.array([T, K, H, I, E_total, size_ep, rank_ep, int(shared)]))
+    print("wrote moe_blockwise", tag, gt.shape)
+
+
+def moe_pertensor_case(tag, T, K, H, I, E_total, size_ep, rank_ep, seed):
+    ns = extract_many(REF / "tests/test_fuse_moe_pertensor.py",
+                      {"naive_gather_expert_inputs", "naive_group_gemm", "naive_act_mul_and_quant",
+                       "naive_reduce", "naive_fuse_moe_pertensor_fp8"})
+    g = torch.Generator().manual_seed(seed)
+    E = E_total // size_ep
+    topk_ids = torch.multinomial(torch.ones((T, E_total)), K, replacement=False, generator=g).to(torch.int32)
+    topk_ids, _ = torch.sort(topk_ids, dim=1)
+    topk_scale = torch.rand((T, K), generator=g)
+    x = torch.randn((T, H), generator=g).to(torch.float8_e4m3fn)
+    guw = torch.randn((E, 2 * I, H), generator=g).to(torch.float8_e4m3fn)
+    dw = torch.randn((E, H, I), generator=g).to(torch.float8_e4m3fn)
+    gus = torch.rand((E,), generator=g) * 0.02
+    ds = torch.rand((E,), generator=g) * 0.02
+    acts = torch.rand((1,), generator=g) + 0.5
+    gt = ns["naive_fuse_moe_pertensor_fp8"](x, guw, dw, gus, ds, acts, topk_ids, topk_scale, rank_ep, None)
+    np.savez_compressed(OUT / f"moe_pertensor_{tag}.npz", x=u8(x), guw=u8(guw), dw=u8(dw),
+                        gus=gus.numpy(), ds=ds.numpy(), acts=acts.numpy(), topk_ids=topk_ids.numpy(),
+                        topk_scale=topk_scale.numpy(), out=gt.float().numpy(),
+                        meta=np.array([T, K, H, I, E_total, size_ep, rank_ep]))
+    print("wrote moe_pertensor", tag, gt.shape)
+
+
 if __name__ == "__main__":
+    moe_blockwise_case("a", 24, 4, 256, 128, 8, 2, 1, True, 41)
+    moe_blockwise_case("b", 48, 8, 256, 256, 8, 1, 0, False, 7)
+    moe_pertensor_case("a", 32, 4, 256, 128, 8, 1, 0, 5)
     decode_fp8_case("b2_nhd", 2, [100, 129], 1, 8, 41, "NHD")
     decode_fp8_case("b5_hnd", 5, [1, 64, 65, 300, 515], 2, 16, 10086, "HND")
     decode_bf16_c1()
