@@ -43,6 +43,7 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kThreads = 384;
 constexpr int kMaxGroups = 512;
 constexpr int kEpiBar = 2;
+constexpr int kTileQ = 4;
 
 struct Params {
   const int* seqlens;      // [G] rows per group
@@ -61,6 +62,7 @@ struct Params {
   int kpad4;
   int scale_tile;  // column padding granule of the transposed activation-scale layout
   int use_bf16_mul;
+  int* tile_counter;  // dynamic tile scheduler (zeroed by the launcher)
 };
 
 __device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float2 f) {
@@ -72,8 +74,10 @@ __device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float2 f)
 }
 
 __device__ __forceinline__ float silu_f(float x) {
-  // x / (1 + exp(-x)) with ex2/rcp approximations (reference src/utils/utils.cuh:300-330)
-  return x * rcp_approx(1.f + exp2_approx(-x * 1.4426950408889634f));
+  // x / (1 + exp(-x)) with ex2.approx / approximate division (relative error ~1e-6, far below
+  // the bf16 / e4m3 granularity around it; reference src/utils/utils.cuh:300-330 does the same).
+  // An IEEE expf + division here costs ~35 % of a Gate-Up tile's MMA time in the epilogue.
+  return __fdividef(x, 1.f + __expf(-x));
 }
 
 __device__ __forceinline__ float bf16_round(float x) {
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stages = smem;
   int* s_cu_tiles = reinterpret_cast<int*>(smem + kStages * kStageBytes);
-  int* s_pad_base = s_cu_tiles + (kMaxGroups + 1);
+  int* s_pad_base = s_cu_tiles + (kMaxGroups + 4);  // keeps everything after 16-B aligned
   int* s_rows = s_pad_base + kMaxGroups;
   int* s_row_start = s_rows + kMaxGroups;
   float* s_amax = reinterpret_cast<float*>(s_row_start + kMaxGroups);  // [2][128]
@@ -137,7 +141,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* empty = bars + kStages;
   uint64_t* part_full = bars + 2 * kStages;
   uint64_t* part_empty = part_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_empty + 2);
+  uint64_t* tq_full = part_empty + 2;   // tile-id queue (kTileQ slots): producer -> consumers
+  uint64_t* tq_empty = tq_full + kTileQ;
+  int* s_tileq = reinterpret_cast<int*>(tq_empty + kTileQ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_tileq + kTileQ);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -186,6 +193,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&part_full[i], 1);
       mbar_init(&part_empty[i], 8);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < kTileQ; i++) {
+      mbar_init(&tq_full[i], 1);
+      mbar_init(&tq_empty[i], 9);  // MMA thread + 8 epilogue warps
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -203,10 +214,29 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // =========================== TMA producer ==========================================
-      const uint64_t pol_w = make_policy_evict_first();  // weights stream through once per m-tile
+      // A rows of a group are re-read by every n-tile -> keep them in L2. Weight tiles are shared
+      // by the 2-3 m-tiles of the same (group, n-tile), which run on neighbouring CTAs at about
+      // the same time -> default policy (evict_first made every m-tile re-read HBM: 2.35x traffic).
+      const uint64_t pol_a = make_policy_evict_last();
       uint32_t it = 0;
+      uint32_t tq = 0;
       TileInfo t;
-      for (int tile = blockIdx.x; decode_tile(sched, tile, t); tile += gridDim.x) {
+      // Dynamic scheduler: tiles are claimed from a global counter, so tiles with neighbouring ids
+      // (the m-tiles sharing one weight tile) start within a short window on different CTAs and
+      // share that weight tile through L2. The id of the next tile is claimed one tile ahead.
+      int next_tile = atomicAdd(p.tile_counter, 1);
+      while (true) {
+        const int tile = next_tile;
+        const bool valid = decode_tile(sched, tile, t);
+        {
+          const uint32_t qs = tq % kTileQ;
+          mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1);
+          s_tileq[qs] = valid ? tile : -1;
+          mbar_arrive(&tq_full[qs]);
+          tq++;
+        }
+        if (!valid) break;
+        next_tile = atomicAdd(p.tile_counter, 1);
         const int nrow0 = kFused ? t.nt * 128 : t.nt * kBN;
         const int nrow1 = kFused ? p.n / 2 + t.nt * 128 : t.nt * kBN + 128;
         for (int kb = 0; kb < KB; kb++, it++) {
@@ -215,9 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
           mbar_arrive_expect_tx(&full[s], kStageBytes);
-          tma_load_2d(a_dst, &tmap_a, &full[s], kb * kBK, t.row0);
-          tma_load_3d_hint(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g, pol_w);
-          tma_load_3d_hint(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g, pol_w);
+          tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+          tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
+          tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -227,8 +257,16 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint64_t bdesc0 = make_smem_desc(smem_u32(stages) + kABytes, 16, 1024, kLayoutSW128);
       uint32_t it = 0;   // K-block counter (smem ring)
       uint32_t acc_it = 0;  // accumulator-buffer use counter
+      uint32_t tq = 0;
       TileInfo t;
-      for (int tile = blockIdx.x; decode_tile(sched, tile, t); tile += gridDim.x) {
+      while (true) {
+        const uint32_t qs = tq % kTileQ;
+        mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
+        const int tile = s_tileq[qs];
+        mbar_arrive(&tq_empty[qs]);
+        tq++;
+        if (tile < 0) break;
+        decode_tile(sched, tile, t);
         for (int kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % kStages;
           const bool new_acc = kBlockwise || kb == 0;
@@ -261,8 +299,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int nblk_per_group = p.n / 128;
 
     uint32_t acc_it = 0;
+    uint32_t tq = 0;
     TileInfo t;
-    for (int tile = blockIdx.x; decode_tile(sched, tile, t); tile += gridDim.x) {
+    while (true) {
+      const uint32_t qs = tq % kTileQ;
+      mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
+      const int tile = s_tileq[qs];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tq_empty[qs]);
+      tq++;
+      if (tile < 0) break;
+      decode_tile(sched, tile, t);
       const bool row_valid = row_local < t.nvalid;
       const int nb0 = kFused ? t.nt : t.nt * 2;
       const int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
@@ -279,37 +326,53 @@ __global__ void __launch_bounds__(kThreads, 1)
         const float* ws0_ptr = p.wscale + (static_cast<long long>(t.g) * nblk_per_group + nb0) * p.kpad4;
         const float* ws1_ptr =
             p.wscale + (static_cast<long long>(t.g) * nblk_per_group + (nb1_valid ? nb1 : nb0)) * p.kpad4;
-        float xs_n = row_valid ? __ldg(xs_ptr) : 0.f;
-        float w0_n = __ldg(ws0_ptr);
-        float w1_n = __ldg(ws1_ptr);
+        // block scales are prefetched two K blocks ahead (L2 latency ~ one MMA block)
+        float xs_q[2], w0_q[2], w1_q[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const bool ok = j < KB;
+          xs_q[j] = (ok && row_valid) ? __ldg(xs_ptr + static_cast<long long>(j) * p.m_pad) : 0.f;
+          w0_q[j] = ok ? __ldg(ws0_ptr + j) : 0.f;
+          w1_q[j] = ok ? __ldg(ws1_ptr + j) : 0.f;
+        }
         for (int kb = 0; kb < KB; kb++, acc_it++) {
-          const float xs = xs_n, w0 = w0_n, w1 = w1_n;
-          if (kb + 1 < KB) {
-            xs_n = row_valid ? __ldg(xs_ptr + static_cast<long long>(kb + 1) * p.m_pad) : 0.f;
-            w0_n = __ldg(ws0_ptr + kb + 1);
-            w1_n = __ldg(ws1_ptr + kb + 1);
+          const float xs = xs_q[kb & 1], w0 = w0_q[kb & 1], w1 = w1_q[kb & 1];
+          if (kb + 2 < KB) {
+            xs_q[kb & 1] = row_valid ? __ldg(xs_ptr + static_cast<long long>(kb + 2) * p.m_pad) : 0.f;
+            w0_q[kb & 1] = __ldg(ws0_ptr + kb + 2);
+            w1_q[kb & 1] = __ldg(ws1_ptr + kb + 2);
           }
           const uint32_t buf = acc_it & 1;
           mbar_wait(&part_full[buf], (acc_it >> 1) & 1);
           tc_fence_after();
           const float f0 = xs * w0, f1 = xs * w1;
+          const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1);
+          const uint32_t base = lane_addr + buf * kBN + wg * 64;
+          // 4 chunks of 32 columns: (half 0: c0, c1), (half 1: c2, c3). TMEM loads are issued two
+          // deep so their latency overlaps the FFMA2s; the accumulator buffer is handed back to
+          // the MMA warp as soon as its last column is in registers.
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(base, ra);
+          tmem_ld_x32(base + 32, rb);
+          tmem_wait_ld();
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const float2 f = make_float2(h ? f1 : f0, h ? f1 : f0);
+          for (int i = 0; i < 16; i++)
+            ffma2(acc[0][i], __uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]), ff0);
+          tmem_ld_x32(base + 128, ra);
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-              uint32_t r[32];
-              tmem_ld_x32(lane_addr + buf * kBN + h * 128 + wg * 64 + c * 32, r);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; i++) {
-                ffma2(acc[h][c * 16 + i], __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), f);
-              }
-            }
-          }
+          for (int i = 0; i < 16; i++)
+            ffma2(acc[0][16 + i], __uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]), ff0);
+          tmem_ld_x32(base + 128 + 32, rb);
+          tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&part_empty[buf]);
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+            ffma2(acc[1][i], __uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]), ff1);
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+            ffma2(acc[1][16 + i], __uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]), ff1);
         }
       } else {
         const uint32_t buf = acc_it & 1;
@@ -387,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           s_amax[wg * 128 + row_local] = amax;
           named_bar_sync(kEpiBar, 256);
           amax = fmaxf(amax, s_amax[(wg ^ 1) * 128 + row_local]);
-          const float scale = amax * (1.f / 448.f);
+          const float scale = amax / 448.f;
           inv = 1.f / (scale + 1e-8f);
           if (row_valid && wg == 0) {
             p.q_scale_t[static_cast<long long>(t.nt) * p.m_pad + t.scol0 + row_local] = scale;
@@ -418,8 +481,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr int kSmemBytes = kStages * kStageBytes + (kMaxGroups + 1 + 3 * kMaxGroups) * 4 + 256 * 4 +
-                           (2 * kStages + 4) * 8 + 16;
+constexpr int kSmemBytes = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGroups) * 4 + 256 * 4 +
+                           (2 * kStages + 4 + 2 * kTileQ) * 8 + kTileQ * 4 + 16;
 
 template <bool kBlockwise, bool kFused>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
@@ -429,7 +492,14 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  kern<<<sm_count(), kThreads, kSmemBytes, stream>>>(ta, tb, p);
+  // tile counters: a small rotating pool so back-to-back launches never share one
+  static int* counters = nullptr;
+  static unsigned launch_no = 0;
+  if (counters == nullptr) HPC_CUDA_CHECK(cudaMalloc(&counters, 64 * sizeof(int)));
+  Params pp = p;
+  pp.tile_counter = counters + (launch_no++ % 64);
+  HPC_CUDA_CHECK(cudaMemsetAsync(pp.tile_counter, 0, sizeof(int), stream));
+  kern<<<sm_count(), kThreads, kSmemBytes, stream>>>(ta, tb, pp);
   HPC_CUDA_CHECK(cudaGetLastError());
   return HPC_OK;
 }
