@@ -62,6 +62,16 @@ lib.hpc_fuse_moe_async.argtypes = [c_ptr] * 23 + [c_int] * 10 + [c_ptr]
 lib.hpc_fuse_moe_blockwise_async.restype = c_int
 lib.hpc_fuse_moe_blockwise_async.argtypes = [c_ptr] * 25 + [c_int] * 12 + [c_ptr]
 
+lib.hpc_fuse_allreduce_rmsnorm_high_throughput_async.restype = c_int
+lib.hpc_fuse_allreduce_rmsnorm_high_throughput_async.argtypes = (
+    [c_ptr] * 8 + [c_i64] * 3 + [ctypes.c_double, c_int, c_int, c_ptr])
+lib.hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async.restype = c_int
+lib.hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async.argtypes = (
+    [c_ptr] * 10 + [c_i64] * 3 + [ctypes.c_double, c_int, c_int, c_ptr])
+lib.hpc_fuse_allreduce_rmsnorm_low_latency_async.restype = c_int
+lib.hpc_fuse_allreduce_rmsnorm_low_latency_async.argtypes = (
+    [c_int] * 4 + [c_ptr] * 4 + [c_int] * 2 + [c_ptr] * 3 + [ctypes.c_double] + [c_ptr] * 2 + [c_int, c_ptr])
+
 lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]

@@ -181,6 +181,32 @@ int hpc_fuse_moe_blockwise_async(
     int num_expert_local, int gate_up_weight_scale_lastdim_pad4, int down_weight_scale_lastdim_pad4,
     int rank_ep, cudaStream_t stream);
 
+/* ---- fused AllReduce + residual + RMSNorm -------------------------------------------------------
+ * High throughput: replaces reference src/allreduce/fuse_allreduce_rmsnorm_high_throughput.h:12-18
+ * (same arguments). `signal_ptr`: device int64[world_size] of signal-pad addresses; `mc_*`: the
+ * NVLS multicast addresses of the slices. The _p2p variant additionally takes HOST int64
+ * tables of every rank's slice address and is used when the fabric offers no multicast mapping
+ * (mc pointers NULL).
+ * Low latency: replaces ...low_latency.h:29-49,503-504 (AllReduceFusionParams flattened;
+ * num_max_blocks 0 = one block per SM).
+ */
+int hpc_fuse_allreduce_rmsnorm_high_throughput_async(
+    const void* input_ptr, const void* mc_input_ptr, const void* in_res_ptr, const void* weight_ptr,
+    void* output_ptr, void* mc_output_ptr, void* out_res_ptr, void* signal_ptr, int64_t rank,
+    int64_t world_size, int64_t num_max_blocks, double rms_norm_eps, int num_tokens,
+    int hidden_size, cudaStream_t stream);
+int hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async(
+    const void* input_ptr, const void* mc_input_ptr, const void* in_res_ptr, const void* weight_ptr,
+    void* output_ptr, void* mc_output_ptr, void* out_res_ptr, void* signal_ptr,
+    const int64_t* peer_input_ptrs_host, const int64_t* peer_output_ptrs_host, int64_t rank,
+    int64_t world_size, int64_t num_max_blocks, double rms_norm_eps, int num_tokens,
+    int hidden_size, cudaStream_t stream);
+int hpc_fuse_allreduce_rmsnorm_low_latency_async(
+    int n_ranks, int rank, int num_tokens, int token_dim, void** buffer_ptrs_dev,
+    void* buffer_ptr_local, void* multicast_ptr, uint32_t* buffer_flags, int rmsnorm_fusion,
+    int launch_with_pdl, const void* input, const void* residual_in, const void* gamma,
+    double epsilon, void* residual_out, void* output, int num_max_blocks, cudaStream_t stream);
+
 /* ---- bring-up self test: one CTA, nk tcgen05.mma (kind::f8f6f4) with caller-supplied smem
  * images and descriptor fields; D[128, ncols] fp32 is copied out of TMEM. Used by tests to pin
  * the UMMA descriptor conventions the kernels rely on. */
