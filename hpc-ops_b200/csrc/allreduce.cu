@@ -202,57 +202,106 @@ struct HtParams {
   float eps;
 };
 
+// reduce one row's vectors over the ranks (fp32) and fetch the matching residual vectors
+__device__ __forceinline__ void ht_load_row(const HtParams& p, int row, int nvec, int vstride,
+                                            int nv_row, float (*s)[8], uint4* res) {
+  const long long roff = static_cast<long long>(row) * p.hidden;
+#pragma unroll
+  for (int j = 0; j < kMaxVecPerThread; j++) {
+    const int v = threadIdx.x + j * vstride;
+    if (j < nvec && v < nv_row) {
+      if (p.world == 1) {
+        unpack8(ld_nc_v4(p.x + roff + v * 8), s[j]);
+      } else if (p.mc_x != nullptr) {
+        unpack8(multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8),
+                s[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[j][i] = 0.f;
+        for (int r = 0; r < p.world; r++) {
+          float t[8];
+          unpack8(ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[r]) + roff + v * 8), t);
+#pragma unroll
+          for (int i = 0; i < 8; i++) s[j][i] += t[i];
+        }
+      }
+      res[j] = ld_nc_v4(p.residual + roff + v * 8);
+    }
+  }
+}
+
+template <int NVEC>
 __global__ void __launch_bounds__(1024)
     ar_rmsnorm_ht_kernel(const HtParams p) {
-  __shared__ float s_red[32];
+  __shared__ float s_red[2][32];
   const int nv_row = p.hidden / 8;
   const int vstride = blockDim.x;
-  const int nvec = (nv_row + vstride - 1) / vstride;
   const int nwarps = blockDim.x / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   if (p.world > 1) block_barrier(nullptr, p.signal_ptrs, p.rank, p.world, blockIdx.x, gridDim.x, 0);
 
-  for (int row = blockIdx.x; row < p.num_tokens; row += gridDim.x) {
+  // software pipeline over this block's rows: the (NVLS) loads of row i+1 are in flight while
+  // row i is normalised and broadcast
+  float s_cur[NVEC][8], s_nxt[NVEC][8];
+  uint4 r_cur[NVEC], r_nxt[NVEC];
+  int row = blockIdx.x;
+  if (row < p.num_tokens) ht_load_row(p, row, NVEC, vstride, nv_row, s_cur, r_cur);
+  int it = 0;
+  for (; row < p.num_tokens; row += gridDim.x, it++) {
+    const int nrow = row + gridDim.x;
+    if (nrow < p.num_tokens) ht_load_row(p, nrow, NVEC, vstride, nv_row, s_nxt, r_nxt);
     const long long roff = static_cast<long long>(row) * p.hidden;
-    float s[kMaxVecPerThread][8];
+    float sq = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxVecPerThread; j++) {
+    for (int j = 0; j < NVEC; j++) {
       const int v = threadIdx.x + j * vstride;
-      if (j < nvec && v < nv_row) {
+      if (v < nv_row) {
+        float r[8], t[8];
+        unpack8(r_cur[j], r);
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = s_cur[j][i] + r[i];
+        const uint4 packed = pack8(t);  // residual_out is bf16; the norm sees the rounded values
+        *reinterpret_cast<uint4*>(p.out_residual + roff + v * 8) = packed;
+        unpack8(packed, s_cur[j]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) sq += s_cur[j][i] * s_cur[j][i];
+      }
+    }
+    sq = warp_sum_f32(sq);
+    float* red = s_red[it & 1];  // double buffered: one __syncthreads per row
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < nwarps; w++) tot += red[w];
+    const float rstd = rsqrtf(tot / static_cast<float>(p.hidden) + p.eps);
+#pragma unroll
+    for (int j = 0; j < NVEC; j++) {
+      const int v = threadIdx.x + j * vstride;
+      if (v < nv_row) {
+        float w[8], n[8];
+        unpack8(ld_nc_v4(p.weight + v * 8), w);
+        // (x * rstd) rounded to bf16, then * gamma in bf16 (reference test rmsnorm():16-19)
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          n[i] = __bfloat162float(__float2bfloat16_rn(s_cur[j][i] * rstd)) * w[i];
+        const uint4 y = pack8(n);
         if (p.world == 1) {
-          unpack8(ld_nc_v4(p.x + roff + v * 8), s[j]);
-        } else if (p.mc_x != nullptr) {
-          unpack8(multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8),
-                  s[j]);
+          *reinterpret_cast<uint4*>(p.out_x + roff + v * 8) = y;
+        } else if (p.mc_out_x != nullptr) {
+          multimem_st_v4(static_cast<__nv_bfloat16*>(p.mc_out_x) + roff + v * 8, y);
         } else {
-#pragma unroll
-          for (int i = 0; i < 8; i++) s[j][i] = 0.f;
           for (int r = 0; r < p.world; r++) {
-            float t[8];
-            unpack8(ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[r]) + roff + v * 8), t);
-#pragma unroll
-            for (int i = 0; i < 8; i++) s[j][i] += t[i];
+            st_sys_v4(reinterpret_cast<__nv_bfloat16*>(p.peer_out[r]) + roff + v * 8, y);
           }
         }
       }
     }
-    uint4 y[kMaxVecPerThread];
-    fuse_row(s, nvec, threadIdx.x, vstride, nv_row, p.residual + roff, p.out_residual + roff,
-             p.weight, p.eps, p.hidden, s_red, nwarps, y);
 #pragma unroll
-    for (int j = 0; j < kMaxVecPerThread; j++) {
-      const int v = threadIdx.x + j * vstride;
-      if (j < nvec && v < nv_row) {
-        if (p.world == 1) {
-          *reinterpret_cast<uint4*>(p.out_x + roff + v * 8) = y[j];
-        } else if (p.mc_out_x != nullptr) {
-          multimem_st_v4(static_cast<__nv_bfloat16*>(p.mc_out_x) + roff + v * 8, y[j]);
-        } else {
-          for (int r = 0; r < p.world; r++) {
-            st_sys_v4(reinterpret_cast<__nv_bfloat16*>(p.peer_out[r]) + roff + v * 8, y[j]);
-          }
-        }
-      }
+    for (int j = 0; j < NVEC; j++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) s_cur[j][i] = s_nxt[j][i];
+      r_cur[j] = r_nxt[j];
     }
   }
   if (p.world > 1) {
@@ -473,7 +522,13 @@ extern "C" int hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async(
   // The grid must be identical on every rank (the barrier pairs block b with block b), so it
   // depends only on num_max_blocks.
   const int grid = static_cast<int>(num_max_blocks);
-  ar::ar_rmsnorm_ht_kernel<<<grid, pick_threads(hidden_size), 0, stream>>>(p);
+  const int threads = pick_threads(hidden_size);
+  const int nvec = (hidden_size / 8 + threads - 1) / threads;
+  switch (nvec) {
+    case 1: ar::ar_rmsnorm_ht_kernel<1><<<grid, threads, 0, stream>>>(p); break;
+    case 2: ar::ar_rmsnorm_ht_kernel<2><<<grid, threads, 0, stream>>>(p); break;
+    default: ar::ar_rmsnorm_ht_kernel<4><<<grid, threads, 0, stream>>>(p); break;
+  }
   HPC_CUDA_CHECK(cudaGetLastError());
   return HPC_OK;
 }
