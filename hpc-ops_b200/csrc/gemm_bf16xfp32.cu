@@ -1,0 +1,318 @@
+// BF16 x "FP32" route GEMM (B200 / sm_100a), written from scratch.
+//
+//   Y[m, n] = X . W_high^T + scale * (X . W_low^T)      X [M, K] bf16, W_high/W_low [N, K] bf16
+//
+// i.e. an fp32-weight GEMM emulated by two bf16 GEMMs sharing one X tile (W = W_high + scale*W_low).
+// Replaces reference src/gemm/sm90/gemm_bf16xfp32.cu:83-407 and its launcher (:488).
+//
+// One CTA per (m-tile 128, n-tile <= 256, k-split): warp 0 = TMA producer (X, W_high, W_low tiles of
+// 64 K-elements = 128 B swizzled rows, 3 stages), warp 1 = tcgen05 issuer (kind::f16, two TMEM
+// accumulators: high and low), warps 2-5 = epilogue (TMEM -> regs, high + scale*low).
+// N is small for this op (192 .. 2048), so the grid is filled by splitting K: partial tiles go to
+// the fp32 workspace `split_y`; the last CTA to arrive on the tile's counter in `split_flag` sums the
+// partials in split order (deterministic), writes Y and resets the counter to zero.
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace b200 {
+namespace rgemm {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // bf16 elements per stage = one 128-byte swizzle row
+constexpr int kMaxStages = 4;
+constexpr int kStageRegion = 196608;  // 192 KB of operand stages, barriers behind it
+constexpr int kThreads = 192;
+
+struct Params {
+  void* y;
+  float* split_y;
+  int* split_flag;
+  int flag_ld;
+  int m, n, k;
+  int tile_n;
+  int split_k;
+  int ksteps_per_split;
+  float scale;
+  int fp32_out;
+  int stages;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_bf16xfp32_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                          const __grid_constant__ CUtensorMap tmap_wh,
+                          const __grid_constant__ CUtensorMap tmap_wl, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int a_bytes = kBM * kBK * 2;        // 16 KB
+  const int b_bytes = p.tile_n * kBK * 2;   // tile_n * 128 B
+  const int stage_bytes = a_bytes + 2 * b_bytes;
+  uint8_t* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStageRegion);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* acc_full = bars + 2 * kMaxStages;
+  const int kStages = p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int mt = blockIdx.x;
+  const int nt = blockIdx.y;
+  const int ks = blockIdx.z;
+  const int total_ksteps = (p.k + kBK - 1) / kBK;
+  const int kstep0 = ks * p.ksteps_per_split;
+  int nsteps = total_ksteps - kstep0;
+  nsteps = nsteps < p.ksteps_per_split ? nsteps : p.ksteps_per_split;
+  if (nsteps < 0) nsteps = 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_wh);
+    prefetch_tensormap(&tmap_wl);
+    for (int i = 0; i < kMaxStages; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nsteps; i++) {
+        const uint32_t s = i % kStages;
+        mbar_wait(&empty[s], ((i / kStages) & 1) ^ 1);
+        uint8_t* a_dst = stages + s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        const int kc = (kstep0 + i) * kBK;
+        tma_load_2d(a_dst, &tmap_x, &full[s], kc, mt * kBM);
+        tma_load_2d(a_dst + a_bytes, &tmap_wh, &full[s], kc, nt * p.tile_n);
+        tma_load_2d(a_dst + a_bytes + b_bytes, &tmap_wl, &full[s], kc, nt * p.tile_n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nsteps > 0) {
+      const uint32_t idesc = make_idesc(kBM, p.tile_n, kFmtBF16, kFmtBF16, 0, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(stages), 16, 1024, kLayoutSW128);
+      const uint64_t bh0 = make_smem_desc(smem_u32(stages) + a_bytes, 16, 1024, kLayoutSW128);
+      const uint64_t bl0 = make_smem_desc(smem_u32(stages) + a_bytes + b_bytes, 16, 1024, kLayoutSW128);
+      for (int i = 0; i < nsteps; i++) {
+        const uint32_t s = i % kStages;
+        mbar_wait(&full[s], (i / kStages) & 1);
+        tc_fence_after();
+        const uint64_t so = static_cast<uint64_t>(s * (stage_bytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // UMMA_K = 16 bf16 = 32 B
+          umma_f16(tmem_base, adesc0 + so + k * 2, bh0 + so + k * 2, idesc, (i | k) != 0);
+          umma_f16(tmem_base + 256, adesc0 + so + k * 2, bl0 + so + k * 2, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---------------- epilogue: thread = output row ----------------
+    const int quad = warp & 3;
+    const int row_local = quad * 32 + lane;
+    const int row = mt * kBM + row_local;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int col0 = nt * p.tile_n;
+    const bool row_ok = row < p.m;
+    if (nsteps > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    float* part = p.split_k > 1
+                      ? p.split_y + (static_cast<long long>(ks) * p.m + row) * p.n + col0
+                      : nullptr;
+    for (int c = 0; c < p.tile_n; c += 16) {
+      float v[16];
+      if (nsteps > 0) {
+        uint32_t hi[16], lo[16];
+        tmem_ld_x16(lane_addr + c, hi);
+        tmem_ld_x16(lane_addr + 256 + c, lo);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(hi[i]) + p.scale * __uint_as_float(lo[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = 0.f;
+      }
+      if (!row_ok) continue;
+      if (p.split_k > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          *reinterpret_cast<float4*>(part + c + i * 4) =
+              make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+        }
+      } else if (p.fp32_out) {
+        float* dst = static_cast<float*>(p.y) + static_cast<long long>(row) * p.n + col0 + c;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          *reinterpret_cast<float4*>(dst + i * 4) =
+              make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+        }
+      } else {
+        __nv_bfloat16* dst =
+            static_cast<__nv_bfloat16*>(p.y) + static_cast<long long>(row) * p.n + col0 + c;
+        uint4 w0, w1;
+        __nv_bfloat162 b[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) b[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w0.x = *reinterpret_cast<uint32_t*>(&b[0]);
+        w0.y = *reinterpret_cast<uint32_t*>(&b[1]);
+        w0.z = *reinterpret_cast<uint32_t*>(&b[2]);
+        w0.w = *reinterpret_cast<uint32_t*>(&b[3]);
+        w1.x = *reinterpret_cast<uint32_t*>(&b[4]);
+        w1.y = *reinterpret_cast<uint32_t*>(&b[5]);
+        w1.z = *reinterpret_cast<uint32_t*>(&b[6]);
+        w1.w = *reinterpret_cast<uint32_t*>(&b[7]);
+        *reinterpret_cast<uint4*>(dst) = w0;
+        *reinterpret_cast<uint4*>(dst + 8) = w1;
+      }
+    }
+    if (p.split_k > 1) {
+      // publish the partial tile, count arrivals; the last CTA reduces in split order
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (warp == 2 && lane == 0) {
+        int* flag = p.split_flag + static_cast<long long>(mt) * p.flag_ld + nt;
+        const int prev = atomicAdd(flag, 1);
+        *s_last = (prev == p.split_k - 1) ? 1 : 0;
+        if (prev == p.split_k - 1) *flag = 0;  // leave the workspace zeroed for the next call
+      }
+      named_bar_sync(1, 128);
+      if (*s_last && row_ok) {
+        __threadfence();
+        for (int c = 0; c < p.tile_n; c += 4) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s = 0; s < p.split_k; s++) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(
+                p.split_y + (static_cast<long long>(s) * p.m + row) * p.n + col0 + c));
+            acc.x += t.x;
+            acc.y += t.y;
+            acc.z += t.z;
+            acc.w += t.w;
+          }
+          if (p.fp32_out) {
+            *reinterpret_cast<float4*>(static_cast<float*>(p.y) + static_cast<long long>(row) * p.n +
+                                       col0 + c) = acc;
+          } else {
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(acc.x, acc.y);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(acc.z, acc.w);
+            uint2 w;
+            w.x = *reinterpret_cast<uint32_t*>(&b0);
+            w.y = *reinterpret_cast<uint32_t*>(&b1);
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.y) +
+                                      static_cast<long long>(row) * p.n + col0 + c) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int pick_tile_n(int n) {
+  if (n % 128 == 0) return 128;  // 4 stages of 48 KB; more n-tiles = more CTAs for this small-N op
+  if (n % 192 == 0) return 192;  // the router shape (N = 192): one n-tile, 3 stages of 64 KB
+  return 64;
+}
+
+}  // namespace rgemm
+}  // namespace b200
+
+using namespace b200;  // NOLINT
+
+// Split-K chosen for an (m, n, k) problem (host helper; the Python layer sizes `split_y` with it).
+// Mirrors the role of reference src/gemm/sm90/entry.cc:25-84 (select_config).
+extern "C" int hpc_gemm_bf16xfp32_select_splitk(int m, int n, int k, int use_splitk) {
+  if (!use_splitk || m <= 0 || n <= 0) return 1;
+  const int tile_n = rgemm::pick_tile_n(n);
+  const int tiles = ((m + rgemm::kBM - 1) / rgemm::kBM) * (n / tile_n);
+  const int ksteps = (k + rgemm::kBK - 1) / rgemm::kBK;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int split = 1;
+  while (split < 16 && tiles * split * 2 <= sms && ksteps / (split * 2) >= 4) split *= 2;
+  return split;
+}
+
+// replaces reference src/gemm/gemm.h:12-15 (gemm_bf16xfp32_async). `tile_m` / `k_warpgroup_n` are
+// the reference's sm_90 tile knobs (accepted, ignored); `flag_ld` is the row stride of split_flag
+// (0 = dense [ceil(m/128), n / tile_n]).
+extern "C" int hpc_gemm_bf16xfp32_async(void* y_ptr, void* split_y_ptr, void* split_flag_ptr,
+                                        const void* x_ptr, const void* w_high_ptr,
+                                        const void* w_low_ptr, int m, int n, int k, float scale,
+                                        int use_fp32_output, int split_k, int tile_m,
+                                        int k_warpgroup_n, int flag_ld, cudaStream_t stream) {
+  (void)tile_m;
+  (void)k_warpgroup_n;
+  HPC_REQUIRE(n % 64 == 0 && n > 0, "gemm_bf16xfp32: n must to be divided by 64.");
+  HPC_REQUIRE(k % 8 == 0 && k > 0, "gemm_bf16xfp32: k (%d) must be a multiple of 8", k);
+  HPC_REQUIRE(split_k >= 1 && split_k <= 64, "gemm_bf16xfp32: bad split_k %d", split_k);
+  if (m <= 0) return HPC_OK;
+  if (split_k > 1) {
+    HPC_REQUIRE(split_y_ptr != nullptr && split_flag_ptr != nullptr,
+                "gemm_bf16xfp32: split-k needs split_y and split_flag workspaces");
+  }
+  const int tile_n = rgemm::pick_tile_n(n);
+  CUtensorMap tx, twh, twl;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(m)};
+    uint64_t strides[1] = {static_cast<uint64_t>(k) * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(rgemm::kBK), static_cast<uint32_t>(rgemm::kBM)};
+    int rc = encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x_ptr, 2, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  for (int which = 0; which < 2; which++) {
+    uint64_t dims[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(n)};
+    uint64_t strides[1] = {static_cast<uint64_t>(k) * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(rgemm::kBK), static_cast<uint32_t>(tile_n)};
+    int rc = encode_tmap(which ? &twl : &twh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         which ? w_low_ptr : w_high_ptr, 2, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  rgemm::Params p;
+  p.y = y_ptr;
+  p.split_y = static_cast<float*>(split_y_ptr);
+  p.split_flag = static_cast<int*>(split_flag_ptr);
+  p.m = m;
+  p.n = n;
+  p.k = k;
+  p.tile_n = tile_n;
+  p.split_k = split_k;
+  const int ksteps = (k + rgemm::kBK - 1) / rgemm::kBK;
+  p.ksteps_per_split = (ksteps + split_k - 1) / split_k;
+  p.scale = scale;
+  p.fp32_out = use_fp32_output;
+  p.flag_ld = flag_ld > 0 ? flag_ld : n / tile_n;
+  const int stage_bytes = rgemm::kBM * rgemm::kBK * 2 + 2 * tile_n * rgemm::kBK * 2;
+  p.stages = rgemm::kStageRegion / stage_bytes;
+  if (p.stages > rgemm::kMaxStages) p.stages = rgemm::kMaxStages;
+  const int smem = rgemm::kStageRegion + 256;
+  static bool configured = false;
+  if (!configured) {
+    HPC_CUDA_CHECK(cudaFuncSetAttribute(rgemm::gemm_bf16xfp32_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((m + rgemm::kBM - 1) / rgemm::kBM, n / tile_n, split_k);
+  rgemm::gemm_bf16xfp32_kernel<<<grid, rgemm::kThreads, smem, stream>>>(tx, twh, twl, p);
+  HPC_CUDA_CHECK(cudaGetLastError());
+  return HPC_OK;
+}

@@ -1,0 +1,634 @@
+// FP8 block-sparse (and dense) causal prefill attention over a paged KV cache (B200 / sm_100a).
+//
+// Replaces reference src/attention/prefill/kernels.cuh:1978-2554 (q per-token/head, k/v per-tensor)
+// and :2558-3150 (q per-token/head, k per-token/head in-cache scales, v per-head), their launcher
+// src/attention/prefill/warp_spec_with_kvcache_blocksparse_fp8_dim128.cu:19-253 and the varlen TMA
+// patch kernel (kernels.cuh:169-215, not needed here: Q is addressed with a 3-D descriptor).
+//
+// Work item = (batch, q head, 128-row Q tile); it visits only the 128x128 KV tiles that are set in
+// block_mask (absolute KV tile index, Q tile index relative to the request's first new token):
+//   active = { j < min(num_tile_kv, Kb) : mask[b, hq, mq, j] } U { Kb if Kb < num_tile_kv }
+// Items are handed out heaviest-first (largest mq first) by a global atomic counter.
+//
+// CTA = 256 threads:
+//   warp 0     : TMA producer (Q tile, K/V pages -> 4-stage ring of 32 KB, k scales when per-token),
+//                builds the active-tile list of each item with ballot compaction
+//   warp 1     : tcgen05 issuer. S[128 q, 128 keys] = Q . K^T (K-major A/B);
+//                O_tile[128 q, 128 d] = P . V with P K-major from smem and V MN-major exactly as it
+//                lies in the cache (no software transpose, unlike wgmma fp8: utils.cuh:461-521)
+//   warps 4-7  : softmax, one thread per query row (row max / sum are thread-local): TMEM -> regs,
+//                scale, causal/length mask, base-2 online softmax, P*256 -> e4m3 into 128B-swizzled
+//                smem, O tile TMEM -> fp32 register accumulator with rescale.
+// TMEM: S and O_tile double buffered (4 x 128 columns).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace b200 {
+namespace prefill {
+
+constexpr int kTile = 128;
+constexpr int kPage = 64;
+constexpr int kD = 128;
+constexpr int kTileBytes = kTile * kD;  // 16 KB fp8
+constexpr int kStages = 4;
+constexpr int kStageBytes = 2 * kTileBytes;
+constexpr int kThreads = 256;
+constexpr int kMaxKvTiles = 1024;  // seq_kv <= 128 K
+constexpr int kSoftmaxBar = 1;
+
+struct Params {
+  const int* cu_seqlens_q;
+  const int* seqlens_kv;
+  const int* block_ids;
+  const uint8_t* block_mask;  // [B, Hq, mask_mq, mask_kb] or NULL
+  const float* qscale;        // [B, Hq, qscale_ld]
+  const float* kscale;        // [1] or per-token [blocks, 2, Hkv, 32]
+  const float* vscale;        // [1] or [Hkv]
+  __nv_bfloat16* out;
+  int* work_counter;
+  long long ks_stride_blk, ks_stride_grp, ks_stride_head;  // per-token k-scale strides (floats)
+  int num_batch, num_head_q, num_head_kv, group;
+  int max_q_tiles;
+  int mask_mq, mask_kb;
+  int max_blocks;
+  int qscale_ld;  // padded q length of qscale
+  int ld_out;     // elements between tokens of out
+  int k_head_first, v_head_first;
+  float softmax_scale_log2;
+};
+
+struct Work {
+  int b, hq, mq;
+  int q0;        // first token row (global) of the tile
+  int rows;      // valid rows
+  int seq_q, seq_kv;
+  int num_tile_kv;  // causal extent of this Q tile in KV tiles
+};
+
+__device__ __forceinline__ bool decode_work(const Params& p, int w, Work& k) {
+  const int per_level = p.num_batch * p.num_head_q;
+  if (w >= p.max_q_tiles * per_level) return false;
+  const int level = w / per_level;
+  const int rem = w - level * per_level;
+  k.mq = p.max_q_tiles - 1 - level;  // heaviest first
+  k.b = rem / p.num_head_q;
+  k.hq = rem - k.b * p.num_head_q;
+  const int s0 = p.cu_seqlens_q[k.b];
+  k.seq_q = p.cu_seqlens_q[k.b + 1] - s0;
+  k.seq_kv = p.seqlens_kv[k.b];
+  k.q0 = s0 + k.mq * kTile;
+  const int left = k.seq_q - k.mq * kTile;
+  k.rows = left < kTile ? left : kTile;
+  if (k.rows <= 0) {
+    k.rows = 0;
+    k.num_tile_kv = 0;
+    return true;  // not an item of this request; caller skips it
+  }
+  long long lim = static_cast<long long>(k.seq_kv) - k.seq_q + (k.mq + 1) * kTile;  // exclusive
+  if (lim > k.seq_kv) lim = k.seq_kv;
+  if (lim < 0) lim = 0;
+  k.num_tile_kv = static_cast<int>((lim + kTile - 1) / kTile);
+  return true;
+}
+
+template <bool kKPerToken>
+struct Smem {
+  static constexpr int kOffStages = 0;
+  static constexpr int kOffQ = kStages * kStageBytes;            // 2 x 16 KB
+  static constexpr int kOffP = kOffQ + 2 * kTileBytes;           // 2 x 16 KB
+  static constexpr int kOffKs = kOffP + 2 * kTileBytes;          // kStages x 128 floats
+  static constexpr int kOffList = kOffKs + kStages * 128 * 4;    // 2 x (kMaxKvTiles + 8) int16
+  static constexpr int kListStride = kMaxKvTiles + 8;
+  static constexpr int kOffBar = kOffList + 2 * kListStride * 2;
+  static constexpr int kNumBars = 3 * kStages + 12;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kTotal = kOffTmem + 64;
+};
+
+template <bool kKPerToken>
+__global__ void __launch_bounds__(kThreads, 1)
+    prefill_blocksparse_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                                   const __grid_constant__ CUtensorMap tmap_k,
+                                   const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+  using L = Smem<kKPerToken>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stages = smem + L::kOffStages;
+  uint8_t* q_smem = smem + L::kOffQ;
+  uint8_t* p_smem = smem + L::kOffP;
+  float* ks_smem = reinterpret_cast<float*>(smem + L::kOffKs);
+  int16_t* lists = reinterpret_cast<int16_t*>(smem + L::kOffList);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
+
+  uint64_t* k_full = bars;
+  uint64_t* v_full = bars + kStages;
+  uint64_t* stage_empty = bars + 2 * kStages;
+  uint64_t* q_full = bars + 3 * kStages;   // [2] work item published (Q landed + list written)
+  uint64_t* q_empty = q_full + 2;          // [2]
+  uint64_t* s_full = q_full + 4;           // [2]
+  uint64_t* p_full = q_full + 6;           // [2]
+  uint64_t* o_full = q_full + 8;           // [2]
+  uint64_t* list_full = q_full + 10;       // [2] producer lanes finished writing the list
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_k);
+    prefetch_tensormap(&tmap_v);
+    for (int i = 0; i < kStages; i++) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&stage_empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1 + 128);  // MMA thread (commit) + softmax threads
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&list_full[i], 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Every role walks the same sequence of work items. The producer claims them from the global
+  // counter and publishes {work id, active-tile count} + the tile list through smem (slot = item
+  // parity), guarded by q_full / q_empty.
+  int* s_work = reinterpret_cast<int*>(tmem_slot + 4);  // [2][2]: work id, number of active tiles
+
+  if (warp == 0) {
+    // =========================== producer ================================================
+    const uint64_t pol_kv = make_policy_evict_last();  // KV of a request is re-read by its q-heads
+    uint32_t n = 0;     // kv tile counter (ring)
+    uint32_t item = 0;  // item counter
+    while (true) {
+      int w = 0;
+      if (lane == 0) w = atomicAdd(p.work_counter, 1);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      Work k;
+      const bool alive = decode_work(p, w, k);
+      if (alive && k.rows == 0) continue;  // Q tile beyond this request
+      const uint32_t slot = item & 1;
+      mbar_wait(&q_empty[slot], ((item >> 1) & 1) ^ 1);
+      int16_t* list = lists + slot * L::kListStride;
+      int nact = 0;
+      if (alive) {
+        // ---- active tile list (ballot compaction, ascending j) ----
+        const int kb = p.block_mask ? p.mask_kb : k.num_tile_kv;
+        const int lim = k.num_tile_kv < kb ? k.num_tile_kv : kb;
+        const uint8_t* mrow =
+            p.block_mask
+                ? p.block_mask + ((static_cast<long long>(k.b) * p.num_head_q + k.hq) * p.mask_mq +
+                                  (k.mq < p.mask_mq ? k.mq : p.mask_mq - 1)) *
+                                     p.mask_kb
+                : nullptr;
+        for (int j0 = 0; j0 < lim; j0 += 32) {
+          const int j = j0 + lane;
+          const bool on = (j < lim) && (mrow == nullptr || mrow[j] != 0);
+          const unsigned m = __ballot_sync(0xffffffffu, on);
+          if (on) list[nact + __popc(m & ((1u << lane) - 1))] = static_cast<int16_t>(j);
+          nact += __popc(m);
+        }
+        if (p.block_mask && kb < k.num_tile_kv) {  // one unconditional tile past the mask width
+          if (lane == 0) list[nact] = static_cast<int16_t>(kb);
+          nact++;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_work[slot * 2] = alive ? w : -1;
+        s_work[slot * 2 + 1] = nact;
+        if (alive) {
+          mbar_arrive_expect_tx(&q_full[slot], kTileBytes);
+          tma_load_3d(q_smem + slot * kTileBytes, &tmap_q, &q_full[slot], 0, k.hq, k.q0);
+        } else {
+          mbar_arrive(&q_full[slot]);
+        }
+      }
+      __syncwarp();
+      item++;
+      if (!alive) break;
+      // ---- K/V tiles of the active list ----
+      const int hkv = k.hq / p.group;
+      const int nblk = (k.seq_kv + kPage - 1) / kPage;
+      const int* ids = p.block_ids + static_cast<long long>(k.b) * p.max_blocks;
+      const int kc1 = p.k_head_first ? hkv : 0, kc2 = p.k_head_first ? 0 : hkv;
+      const int vc1 = p.v_head_first ? hkv : 0, vc2 = p.v_head_first ? 0 : hkv;
+      for (int i0 = 0; i0 < nact; i0 += 16) {
+        // lanes 2t / 2t+1 fetch the two page ids of tile i0+t
+        const int ti = i0 + (lane >> 1);
+        int id = 0;
+        if (ti < nact) {
+          int blk = static_cast<int>(list[ti]) * 2 + (lane & 1);
+          blk = blk < nblk ? blk : nblk - 1;  // a missing 2nd page re-reads the 1st (keys masked)
+          id = __ldg(ids + blk);
+        }
+        const int cnt = (nact - i0) < 16 ? (nact - i0) : 16;
+        for (int t = 0; t < cnt; t++) {
+          const int id0 = __shfl_sync(0xffffffffu, id, 2 * t);
+          const int id1 = __shfl_sync(0xffffffffu, id, 2 * t + 1);
+          if (lane == 0) {
+            const uint32_t st = n % kStages;
+            mbar_wait(&stage_empty[st], ((n / kStages) & 1) ^ 1);
+            uint8_t* dst = stages + st * kStageBytes;
+            mbar_arrive_expect_tx(&k_full[st], kTileBytes + (kKPerToken ? 512 : 0));
+            tma_load_4d_hint(dst, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_kv);
+            tma_load_4d_hint(dst + kTileBytes / 2, &tmap_k, &k_full[st], 0, kc1, kc2, id1, pol_kv);
+            if constexpr (kKPerToken) {
+              // scales of token t of a page: kscale[page, t / 32, hkv, t % 32]
+              float* kd = ks_smem + st * 128;
+              const float* s0 = p.kscale + id0 * p.ks_stride_blk + hkv * p.ks_stride_head;
+              const float* s1 = p.kscale + id1 * p.ks_stride_blk + hkv * p.ks_stride_head;
+              bulk_load_1d(kd, s0, 128, &k_full[st]);
+              bulk_load_1d(kd + 32, s0 + p.ks_stride_grp, 128, &k_full[st]);
+              bulk_load_1d(kd + 64, s1, 128, &k_full[st]);
+              bulk_load_1d(kd + 96, s1 + p.ks_stride_grp, 128, &k_full[st]);
+            }
+            mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+            tma_load_4d_hint(dst + kTileBytes, &tmap_v, &v_full[st], 0, vc1, vc2, id0, pol_kv);
+            tma_load_4d_hint(dst + kTileBytes + kTileBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2,
+                             id1, pol_kv);
+          }
+          n++;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== tcgen05 issuer (one thread) ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 1);
+      const uint64_t kdesc0 = make_smem_desc(smem_u32(stages), 16, 1024, kLayoutSW128);
+      const uint64_t vdesc0 = make_smem_desc(smem_u32(stages) + kTileBytes, 16, 1024, kLayoutSW128);
+      const uint64_t qdesc0 = make_smem_desc(smem_u32(q_smem), 16, 1024, kLayoutSW128);
+      const uint64_t pdesc0 = make_smem_desc(smem_u32(p_smem), 16, 1024, kLayoutSW128);
+
+      auto issue_pv = [&](uint32_t m) {
+        const uint32_t st = m % kStages;
+        const uint32_t buf = m & 1;
+        mbar_wait(&p_full[buf], (m >> 1) & 1);
+        mbar_wait(&v_full[st], (m / kStages) & 1);
+        tc_fence_after();
+        const uint64_t ad = pdesc0 + static_cast<uint64_t>(buf * (kTileBytes >> 4));
+        const uint64_t bd = vdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
+        const uint32_t d = tmem_base + 256 + buf * 128;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
+          umma_f8(d, ad + k * 2, bd + k * (4096 >> 4), idesc_pv, k > 0);
+        }
+        umma_commit(&stage_empty[st]);
+        umma_commit(&o_full[buf]);
+      };
+
+      uint32_t n = 0;
+      uint32_t item = 0;
+      while (true) {
+        const uint32_t slot = item & 1;
+        mbar_wait(&q_full[slot], (item >> 1) & 1);
+        const int w = s_work[slot * 2];
+        const int nact = s_work[slot * 2 + 1];
+        if (w < 0) break;
+        const uint64_t ad = qdesc0 + static_cast<uint64_t>(slot * (kTileBytes >> 4));
+        for (int i = 0; i < nact; i++) {
+          const uint32_t st = n % kStages;
+          const uint32_t buf = n & 1;
+          mbar_wait(&k_full[st], (n / kStages) & 1);
+          tc_fence_after();
+          const uint64_t bd = kdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
+          const uint32_t d = tmem_base + buf * 128;
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_f8(d, ad + k * 2, bd + k * 2, idesc_qk, k > 0);
+          umma_commit(&s_full[buf]);
+          if (n > 0) issue_pv(n - 1);
+          n++;
+        }
+        // Q tile (and the list slot) may be overwritten once every QK of the item has completed
+        umma_commit(&q_empty[slot]);
+        item++;
+      }
+      if (n > 0) issue_pv(n - 1);
+    }
+  } else if (warp >= 4) {
+    // =========================== softmax / epilogue =======================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // query row of the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float ks_tensor = kKPerToken ? 1.f : p.kscale[0];
+
+    uint32_t n = 0;
+    uint32_t item = 0;
+    while (true) {
+      const uint32_t slot = item & 1;
+      mbar_wait(&q_full[slot], (item >> 1) & 1);
+      const int w = s_work[slot * 2];
+      const int nact = s_work[slot * 2 + 1];
+      if (w < 0) break;
+      Work k;
+      decode_work(p, w, k);
+      const int16_t* list = lists + slot * L::kListStride;
+      const int hkv = k.hq / p.group;
+      const bool row_ok = row < k.rows;
+      const float qs = row_ok ? __ldg(p.qscale + (static_cast<long long>(k.b) * p.num_head_q + k.hq) *
+                                                      p.qscale_ld + k.mq * kTile + row)
+                              : 0.f;
+      const float cq = qs * ks_tensor * p.softmax_scale_log2;
+      // kv positions visible to this row: pos <= row_lim and pos < seq_kv
+      const int row_lim = k.seq_kv - k.seq_q + k.mq * kTile + row;
+      const int tile_lim_min = k.seq_kv - k.seq_q + k.mq * kTile;  // row 0
+      float mrun = -INFINITY, lrun = 0.f, alpha_pend = 1.f;
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 128; i++) acc[i] = 0.f;
+
+      auto consume_o = [&](uint32_t m) {
+        const uint32_t buf = m & 1;
+        mbar_wait(&o_full[buf], (m >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t o[32];
+          tmem_ld_x32(lane_addr + 256 + buf * 128 + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[c * 32 + i] = acc[c * 32 + i] * alpha_pend + __uint_as_float(o[i]);
+        }
+      };
+
+      for (int i = 0; i < nact; i++) {
+        const int j = list[i];
+        const uint32_t buf = n & 1;
+        const uint32_t st = n % kStages;
+        mbar_wait(&s_full[buf], (n >> 1) & 1);
+        tc_fence_after();
+        const int key0 = j * kTile;
+        const bool need_mask = (key0 + kTile - 1 > tile_lim_min) || (key0 + kTile > k.seq_kv);
+        const float* ksr = ks_smem + st * 128;
+        // ---- pass 1: row max ----
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t sr[32];
+          tmem_ld_x32(lane_addr + buf * 128 + c * 32, sr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e++) {
+            float v = __uint_as_float(sr[e]) * cq;
+            if constexpr (kKPerToken) v *= ksr[c * 32 + e];
+            if (need_mask) {
+              const int pos = key0 + c * 32 + e;
+              v = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v;
+            }
+            mx = fmaxf(mx, v);
+          }
+        }
+        if (!row_ok) mx = -INFINITY;
+        const float mnew = fmaxf(mrun, mx);
+        const bool dead = (mnew == -INFINITY);
+        const float alpha = dead ? 1.f : exp2_approx(mrun - mnew);
+        // ---- pass 2: P = exp2(s - m) ; sum ; P*256 -> e4m3 -> swizzled smem row ----
+        float psum = 0.f;
+        uint8_t* prow = p_smem + buf * kTileBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t sr[32];
+          tmem_ld_x32(lane_addr + buf * 128 + c * 32, sr);
+          tmem_wait_ld();
+          uint32_t packed[8];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; q4++) {
+            float e4[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              const int e = q4 * 4 + t;
+              float v = __uint_as_float(sr[e]) * cq;
+              if constexpr (kKPerToken) v *= ksr[c * 32 + e];
+              if (need_mask) {
+                const int pos = key0 + c * 32 + e;
+                v = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v;
+              }
+              const float pe = dead ? 0.f : exp2_approx(v - mnew);
+              psum += pe;
+              e4[t] = pe * 256.f;
+            }
+            packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
+          }
+          // 32 keys = two 16-B chunks (2c, 2c+1) of this row, 128B swizzle: chunk ^ (row & 7)
+          *reinterpret_cast<uint4*>(prow + (((2 * c) ^ (row & 7)) << 4)) =
+              make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ (row & 7)) << 4)) =
+              make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+        mrun = mnew;
+        lrun = lrun * alpha + psum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[buf]);
+
+        if (i > 0) consume_o(n - 1);
+        alpha_pend = alpha;
+        n++;
+      }
+      if (nact > 0) consume_o(n - 1);
+      mbar_arrive(&q_empty[slot]);  // done with the list / work slot
+
+      // ---- epilogue: 1/sum, v scale, bf16 row out ----
+      if (row_ok) {
+        const float vs = (kKPerToken ? __ldg(p.vscale + hkv) : p.vscale[0]) * (1.f / 256.f);
+        // a row whose every visible tile was skipped has sum 0 -> NaN, as documented for the
+        // reference (hpc/attention.py:274-277)
+        const float inv = vs / lrun;
+        __nv_bfloat16* dst = p.out + static_cast<long long>(k.q0 + row) * p.ld_out + k.hq * kD;
+#pragma unroll
+        for (int v8 = 0; v8 < 16; v8++) {
+          uint4 wv;
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[v8 * 8 + 0] * inv, acc[v8 * 8 + 1] * inv);
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(acc[v8 * 8 + 2] * inv, acc[v8 * 8 + 3] * inv);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[v8 * 8 + 4] * inv, acc[v8 * 8 + 5] * inv);
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(acc[v8 * 8 + 6] * inv, acc[v8 * 8 + 7] * inv);
+          wv.x = *reinterpret_cast<uint32_t*>(&b0);
+          wv.y = *reinterpret_cast<uint32_t*>(&b1);
+          wv.z = *reinterpret_cast<uint32_t*>(&b2);
+          wv.w = *reinterpret_cast<uint32_t*>(&b3);
+          *reinterpret_cast<uint4*>(dst + v8 * 8) = wv;
+        }
+      }
+      item++;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace prefill
+}  // namespace b200
+
+using namespace b200;  // NOLINT
+
+static int encode_cache_map(CUtensorMap* tm, const void* base, int heads, int num_blocks,
+                            int64_t blk_stride, int64_t tok_stride, int64_t head_stride,
+                            int* head_first) {
+  *head_first = head_stride <= tok_stride ? 1 : 0;
+  uint64_t dims[4];
+  uint64_t strides[3];
+  uint32_t box[4];
+  dims[0] = 128;
+  box[0] = 128;
+  if (*head_first) {
+    dims[1] = static_cast<uint64_t>(heads);
+    dims[2] = 64;
+    strides[0] = static_cast<uint64_t>(head_stride);
+    strides[1] = static_cast<uint64_t>(tok_stride);
+    box[1] = 1;
+    box[2] = 64;
+  } else {
+    dims[1] = 64;
+    dims[2] = static_cast<uint64_t>(heads);
+    strides[0] = static_cast<uint64_t>(tok_stride);
+    strides[1] = static_cast<uint64_t>(head_stride);
+    box[1] = 64;
+    box[2] = 1;
+  }
+  dims[3] = static_cast<uint64_t>(num_blocks);
+  strides[2] = static_cast<uint64_t>(blk_stride);
+  box[3] = 1;
+  const CUtensorMapL2promotion promo = (tok_stride == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                           : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  return encode_tmap_u8(tm, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, promo);
+}
+
+// Common launcher of the two quant schemes.
+static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, const void* kcache_ptr,
+                          const void* vcache_ptr, const float* qscale_ptr, const float* kscale_ptr,
+                          const float* vscale_ptr, const int* cu_seqlens_q_ptr,
+                          const int* block_ids_ptr, const int* seqlens_kv_ptr,
+                          const uint8_t* block_mask_ptr, int num_batch, int total_seq_q,
+                          int max_seq_q, int num_head_q, int num_head_kv, int num_dim,
+                          int num_kvcache_blocks, int block_size, int max_blocks, int qscale_ld,
+                          int mask_mq, int mask_kb, int ldY, int ldQ, int64_t k_blk, int64_t k_tok,
+                          int64_t k_head, int64_t v_blk, int64_t v_tok, int64_t v_head,
+                          int64_t ks_blk, int64_t ks_grp, int64_t ks_head, cudaStream_t stream) {
+  HPC_REQUIRE(num_dim == 128, "blocksparse prefill: head dim must be 128");
+  HPC_REQUIRE(block_size == 64, "blocksparse prefill: paged block size must be 64 in this build");
+  HPC_REQUIRE(num_head_kv > 0 && num_head_q % num_head_kv == 0, "bad head counts");
+  HPC_REQUIRE(num_batch > 0 && max_seq_q > 0, "bad batch / max_seqlens_q");
+  HPC_REQUIRE((ldQ % 16) == 0 && (reinterpret_cast<uintptr_t>(q_ptr) & 15) == 0, "q alignment");
+  if (total_seq_q <= 0) return HPC_OK;
+
+  CUtensorMap tq, tk, tv;
+  {
+    uint64_t dims[3] = {128, static_cast<uint64_t>(num_head_q), static_cast<uint64_t>(total_seq_q)};
+    uint64_t strides[2] = {128, static_cast<uint64_t>(ldQ)};
+    uint32_t box[3] = {128, 1, 128};
+    int rc = encode_tmap_u8(&tq, q_ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+  }
+  int khf = 1, vhf = 1;
+  int rc = encode_cache_map(&tk, kcache_ptr, num_head_kv, num_kvcache_blocks, k_blk, k_tok, k_head, &khf);
+  if (rc) return rc;
+  rc = encode_cache_map(&tv, vcache_ptr, num_head_kv, num_kvcache_blocks, v_blk, v_tok, v_head, &vhf);
+  if (rc) return rc;
+
+  static int* counters = nullptr;
+  static unsigned launch_no = 0;
+  if (counters == nullptr) HPC_CUDA_CHECK(cudaMalloc(&counters, 64 * sizeof(int)));
+  int* counter = counters + (launch_no++ % 64);
+  HPC_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+
+  prefill::Params p;
+  p.cu_seqlens_q = cu_seqlens_q_ptr;
+  p.seqlens_kv = seqlens_kv_ptr;
+  p.block_ids = block_ids_ptr;
+  p.block_mask = block_mask_ptr;
+  p.qscale = qscale_ptr;
+  p.kscale = kscale_ptr;
+  p.vscale = vscale_ptr;
+  p.out = static_cast<__nv_bfloat16*>(y_ptr);
+  p.work_counter = counter;
+  p.ks_stride_blk = ks_blk;
+  p.ks_stride_grp = ks_grp;
+  p.ks_stride_head = ks_head;
+  p.num_batch = num_batch;
+  p.num_head_q = num_head_q;
+  p.num_head_kv = num_head_kv;
+  p.group = num_head_q / num_head_kv;
+  p.max_q_tiles = (max_seq_q + prefill::kTile - 1) / prefill::kTile;
+  p.mask_mq = mask_mq;
+  p.mask_kb = mask_kb;
+  p.max_blocks = max_blocks;
+  p.qscale_ld = qscale_ld;
+  p.ld_out = ldY;
+  p.k_head_first = khf;
+  p.v_head_first = vhf;
+  p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(128.f);
+
+  const int grid = sm_count();
+  if (k_per_token) {
+    auto kern = prefill::prefill_blocksparse_fp8_kernel<true>;
+    static bool cfg = false;
+    if (!cfg) {
+      HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prefill::Smem<true>::kTotal));
+      cfg = true;
+    }
+    kern<<<grid, prefill::kThreads, prefill::Smem<true>::kTotal, stream>>>(tq, tk, tv, p);
+  } else {
+    auto kern = prefill::prefill_blocksparse_fp8_kernel<false>;
+    static bool cfg = false;
+    if (!cfg) {
+      HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prefill::Smem<false>::kTotal));
+      cfg = true;
+    }
+    kern<<<grid, prefill::kThreads, prefill::Smem<false>::kTotal, stream>>>(tq, tk, tv, p);
+  }
+  HPC_CUDA_CHECK(cudaGetLastError());
+  return HPC_OK;
+}
+
+#define PREFILL_PARAMS                                                                             \
+  void *y_ptr, const void *q_ptr, const void *kcache_ptr, const void *vcache_ptr,                 \
+      const float *qscale_ptr, const float *kscale_ptr, const float *vscale_ptr,                  \
+      const int *cu_seqlens_q_ptr, const int *block_ids_ptr, const int *seqlens_kv_ptr,           \
+      const uint8_t *block_mask_ptr, int num_batch, int total_seq_q, int max_seq_q,               \
+      int num_head_q, int num_head_kv, int num_dim, int num_kvcache_blocks, int block_size,       \
+      int max_blocks, int qscale_ld, int mask_mq, int mask_kb, int ldY, int ldQ, int64_t k_blk,   \
+      int64_t k_tok, int64_t k_head, int64_t v_blk, int64_t v_tok, int64_t v_head
+#define PREFILL_ARGS                                                                               \
+  y_ptr, q_ptr, kcache_ptr, vcache_ptr, qscale_ptr, kscale_ptr, vscale_ptr, cu_seqlens_q_ptr,     \
+      block_ids_ptr, seqlens_kv_ptr, block_mask_ptr, num_batch, total_seq_q, max_seq_q,           \
+      num_head_q, num_head_kv, num_dim, num_kvcache_blocks, block_size, max_blocks, qscale_ld,    \
+      mask_mq, mask_kb, ldY, ldQ, k_blk, k_tok, k_head, v_blk, v_tok, v_head
+
+// replaces reference src/attention/prefill/prefill.h:46-54
+// (attention_with_kvcache_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async)
+extern "C" int hpc_attention_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async(
+    PREFILL_PARAMS, cudaStream_t stream) {
+  return prefill_launch(false, PREFILL_ARGS, 0, 0, 0, stream);
+}
+
+// replaces reference src/attention/prefill/prefill.h:55-63
+// (attention_with_kvcache_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async);
+// ks_* = strides in floats of the k-scale tensor [blocks, block/32, Hkv, 32]
+extern "C" int hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async(
+    PREFILL_PARAMS, int64_t ks_blk, int64_t ks_grp, int64_t ks_head, cudaStream_t stream) {
+  HPC_REQUIRE(ks_grp % 4 == 0 && ks_head % 4 == 0 && ks_blk % 4 == 0,
+              "k scale strides must be multiples of 4 floats (16-byte bulk copies)");
+  return prefill_launch(true, PREFILL_ARGS, ks_blk, ks_grp, ks_head, stream);
+}

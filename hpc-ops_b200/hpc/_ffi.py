@@ -72,6 +72,19 @@ lib.hpc_fuse_allreduce_rmsnorm_low_latency_async.restype = c_int
 lib.hpc_fuse_allreduce_rmsnorm_low_latency_async.argtypes = (
     [c_int] * 4 + [c_ptr] * 4 + [c_int] * 2 + [c_ptr] * 3 + [ctypes.c_double] + [c_ptr] * 2 + [c_int, c_ptr])
 
+lib.hpc_gemm_bf16xfp32_select_splitk.restype = c_int
+lib.hpc_gemm_bf16xfp32_select_splitk.argtypes = [c_int] * 4
+lib.hpc_gemm_bf16xfp32_async.restype = c_int
+lib.hpc_gemm_bf16xfp32_async.argtypes = [c_ptr] * 6 + [c_int] * 3 + [c_f32] + [c_int] * 5 + [c_ptr]
+
+_prefill_args = [c_ptr] * 11 + [c_int] * 14 + [c_i64] * 6
+lib.hpc_attention_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async.restype = c_int
+lib.hpc_attention_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async.argtypes = (
+    _prefill_args + [c_ptr])
+lib.hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async.restype = c_int
+lib.hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async.argtypes = (
+    _prefill_args + [c_i64] * 3 + [c_ptr])
+
 lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]

@@ -165,6 +165,78 @@ def _assign_task_cuda(num_seq_kvcache, num_head_kv, num_seq_q, new_kv_included, 
     return task_map
 
 
+def _blocksparse_prefill_impl(q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids,
+                              seqlens_kvcache, max_seqlens_q, quant_type, block_mask, output):
+    # validation follows reference src/attention/entry.cc:266-409
+    for t, name in ((q, "q"), (kcache, "kcache"), (vcache, "vcache"), (qscale, "qscale"),
+                    (cu_seqlens_q, "cu_seqlens_q"), (block_ids, "block_ids"),
+                    (seqlens_kvcache, "seqlens_kvcache")):
+        _require(t.is_cuda, f"{name} tensor must be cuda")
+    _require(q.dtype == torch.float8_e4m3fn, "q dtype must be fp8_e4m3fn")
+    _require(kcache.element_size() == 1 and vcache.element_size() == 1, "kv cache must be fp8")
+    _require(qscale.dtype == torch.float32 and qscale.is_contiguous(), "qscale must be contiguous float32")
+    _require(cu_seqlens_q.dtype == torch.int32 and block_ids.dtype == torch.int32
+             and seqlens_kvcache.dtype == torch.int32, "index tensors must be int32")
+    _require(block_ids.is_contiguous(), "block_ids tensor must be contiguous")
+    _require(quant_type in (0, 1), "blocksparse prefill supports quant_type 0 and 1")
+    total_seq, num_head_q, dim = q.shape
+    _require(dim == 128, "we only support head dim 128.")
+    _require(q.stride(2) == 1 and q.stride(1) == dim, "q must be contiguous in (head, dim)")
+    num_blocks, block_size, num_head_kv = kcache.size(0), kcache.size(1), kcache.size(2)
+    _require(128 % block_size == 0, "128 must be divisible by the kv block size")
+    _require(kcache.stride(3) == 1 and vcache.stride(3) == 1, "kv cache innermost dim must be contiguous")
+    num_batch = seqlens_kvcache.size(0)
+    _require(cu_seqlens_q.numel() == num_batch + 1, "cu_seqlens_q must have num_batch + 1 entries")
+    _require(qscale.dim() == 3 and qscale.size(0) == num_batch and qscale.size(1) == num_head_q,
+             "qscale shape must be [num_batch, num_head_q, max_seq_q_pad]")
+    mask_ptr, mask_mq, mask_kb = None, 0, 0
+    if block_mask is not None:
+        _require(block_mask.is_cuda and block_mask.is_contiguous() and block_mask.dtype == torch.uint8,
+                 "block_mask must be a contiguous cuda uint8 tensor")
+        _require(block_mask.dim() == 4 and block_mask.size(0) == num_batch
+                 and block_mask.size(1) == num_head_q
+                 and block_mask.size(2) >= (max_seqlens_q + 127) // 128,
+                 "block_mask shape must be [num_batch, num_head_q, ceil(max_seq_q/128), num_kv_tiles]")
+        mask_ptr, mask_mq, mask_kb = block_mask.data_ptr(), block_mask.size(2), block_mask.size(3)
+    if output is not None:
+        _require(output.dtype == torch.bfloat16 and output.is_cuda
+                 and tuple(output.shape) == (total_seq, num_head_q, dim) and output.stride(2) == 1
+                 and output.stride(1) == dim, "output must be bf16 [total_seq, num_head_q, 128]")
+        y = output
+    else:
+        y = torch.empty((total_seq, num_head_q, dim), dtype=torch.bfloat16, device=q.device)
+    common = (
+        _ptr(y), _ptr(q), _ptr(kcache), _ptr(vcache), _ptr(qscale), None, _ptr(vscale),
+        _ptr(cu_seqlens_q), _ptr(block_ids), _ptr(seqlens_kvcache), mask_ptr, num_batch, total_seq,
+        int(max_seqlens_q), num_head_q, num_head_kv, dim, num_blocks, block_size, block_ids.size(1),
+        qscale.size(2), mask_mq, mask_kb, y.stride(0), q.stride(0), kcache.stride(0),
+        kcache.stride(1), kcache.stride(2), vcache.stride(0), vcache.stride(1), vcache.stride(2))
+    if quant_type == 1:
+        _require(kscale.dtype == torch.float32 and vscale.dtype == torch.float32, "scales must be float32")
+        args = common[:5] + (_ptr(kscale),) + common[6:] + (_stream_of(q),)
+        _check_rc(_lib.hpc_attention_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async(*args),
+                  "attention_with_kvcache_blocksparse_prefill_fp8")
+    else:
+        ks = kscale if kscale.dtype == torch.float32 else kscale.view(torch.float32)
+        _require(ks.dim() == 4 and ks.size(0) == num_blocks and ks.size(1) == block_size // 32
+                 and ks.size(2) == num_head_kv and ks.size(3) == 32 and ks.stride(3) == 1,
+                 "per-token kscale must be f32 [num_blocks, block_size/32, num_head_kv, 32]")
+        _require(vscale.dtype == torch.float32 and vscale.numel() == num_head_kv,
+                 "per-head vscale must be f32 [num_head_kv]")
+        args = common[:5] + (_ptr(ks),) + common[6:] + (ks.stride(0), ks.stride(1), ks.stride(2),
+                                                        _stream_of(q))
+        _check_rc(_lib.hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async(*args),
+                  "attention_with_kvcache_blocksparse_prefill_fp8")
+    return y
+
+
+_ops.define(
+    "attention_with_kvcache_blocksparse_prefill_fp8(Tensor q, Tensor kcache, Tensor vcache,"
+    "Tensor qscale, Tensor kscale, Tensor vscale, Tensor cu_seqlens_q,"
+    "Tensor block_ids, Tensor num_seq_kvcache, int max_seqlens_q, int quant_type,"
+    "Tensor? block_mask, Tensor? output) -> (Tensor)")
+_ops.impl("attention_with_kvcache_blocksparse_prefill_fp8", _blocksparse_prefill_impl, "CUDA")
+
 _ops.define(
     "attention_decode_fp8(Tensor q, Tensor! kcache, Tensor! vcache, Tensor block_ids, Tensor "
     "num_seq_kvcache, Tensor qscale, Tensor kscale, Tensor vscale, int mtp, bool "
@@ -182,6 +254,37 @@ _ops.impl("assign_attention_decode_task", _assign_task_cuda, "CUDA")
 # --------------------------------------------------------------------------------------------
 # public API (signatures of reference hpc/attention.py)
 # --------------------------------------------------------------------------------------------
+def attention_with_kvcache_blocksparse_prefill_fp8(
+    q: Tensor,
+    kcache: Tensor,
+    vcache: Tensor,
+    qscale: Tensor,
+    kscale: Tensor,
+    vscale: Tensor,
+    cu_seqlens_q: Tensor,
+    block_ids: Tensor,
+    seqlens_kvcache: Tensor,
+    max_seqlens_q: int,
+    quant_type: QuantType = QuantType.QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR,
+    block_mask: _Optional[Tensor] = None,
+    output: Tensor = None,
+) -> Tensor:
+    """Unified dense / block-sparse causal prefill over the paged FP8 KV cache
+    (contract of reference hpc/attention.py:253-338).
+
+      q [total_seq, Hq, 128] e4m3; caches [blocks, 64, Hkv, 128] e4m3 (NHD or HND via strides);
+      qscale f32 [B, Hq, max_seq_q_pad]; cu_seqlens_q [B+1]; block_ids [B, max_blocks];
+      seqlens_kvcache [B] = total kv tokens (incl. the new ones);
+      block_mask u8 [B, Hq, ceil(max_seq_q/128), Kb] (absolute 128-key tile index; 1 = compute) or
+      None for dense. quant_type 1: kscale/vscale [1]; quant_type 0: kscale f32
+      [blocks, 2, Hkv, 32] (may be passed viewed as fp8), vscale [Hkv].
+    Returns bf16 [total_seq, Hq, 128]. A Q tile with no active KV tile yields NaN rows, as in the
+    reference."""
+    return torch.ops.hpc.attention_with_kvcache_blocksparse_prefill_fp8(
+        q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids, seqlens_kvcache,
+        max_seqlens_q, quant_type.value, block_mask, output)
+
+
 def attention_decode_fp8(
     q: Tensor,
     kcache: Tensor,
@@ -313,6 +416,14 @@ def print_attention_decode_task(task_map: Tensor) -> None:
                   f"num_tile_full:{r[7]}, is_casual_chunk:{r[8]}")
             gid += 1
     print(f"[idle] {empty}/{num_total_ctas} bins were empty")
+
+
+@torch.library.register_fake("hpc::attention_with_kvcache_blocksparse_prefill_fp8")
+def _blocksparse_prefill_fake(q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids,
+                              num_seq_kvcache, max_seqlens_q, quant_type, block_mask, output):
+    if output is not None:
+        return output
+    return torch.empty((q.size(0), q.size(1), vcache.size(3)), dtype=torch.bfloat16, device=q.device)
 
 
 @torch.library.register_fake("hpc::attention_decode_fp8")

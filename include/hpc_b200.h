@@ -207,6 +207,46 @@ int hpc_fuse_allreduce_rmsnorm_low_latency_async(
     int launch_with_pdl, const void* input, const void* residual_in, const void* gamma,
     double epsilon, void* residual_out, void* output, int num_max_blocks, cudaStream_t stream);
 
+/* ---- BF16 x "FP32" route GEMM ---------------------------------------------------------------------
+ * replaces reference src/gemm/gemm.h:12-15 (gemm_bf16xfp32_async):
+ *   Y[m, n] = X . W_high^T + scale * (X . W_low^T), fp32 accumulate, bf16 or fp32 output.
+ * split_k > 1 needs split_y f32 [split_k, m, n] and a zeroed int32 split_flag (left zeroed);
+ * flag_ld = row stride of split_flag in ints (0 = dense). tile_m / k_warpgroup_n: sm_90 tile knobs
+ * of the reference signature, accepted and ignored. hpc_gemm_bf16xfp32_select_splitk is the
+ * heuristic the host uses to size split_y (role of reference src/gemm/sm90/entry.cc:25-84).
+ */
+int hpc_gemm_bf16xfp32_select_splitk(int m, int n, int k, int use_splitk);
+int hpc_gemm_bf16xfp32_async(void* y_ptr, void* split_y_ptr, void* split_flag_ptr,
+                             const void* x_ptr, const void* w_high_ptr, const void* w_low_ptr,
+                             int m, int n, int k, float scale, int use_fp32_output, int split_k,
+                             int tile_m, int k_warpgroup_n, int flag_ld, cudaStream_t stream);
+
+/* ---- FP8 block-sparse / dense causal prefill over the paged KV cache ------------------------------
+ * replace reference src/attention/prefill/prefill.h:46-63. q e4m3 [total_seq_q, Hq, 128] (ldQ =
+ * token stride), caches [blocks, 64, Hkv, 128] e4m3 with element strides (blk, tok, head),
+ * qscale f32 [B, Hq, qscale_ld], out bf16 (ldY = token stride), block_mask u8
+ * [B, Hq, mask_mq, mask_kb] or NULL (dense). kv-per-tensor: kscale/vscale f32[1];
+ * k-per-token: kscale f32 [blocks, 2, Hkv, 32] with strides (ks_blk, ks_grp, ks_head) in floats,
+ * vscale f32 [Hkv].
+ */
+int hpc_attention_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async(
+    void* y_ptr, const void* q_ptr, const void* kcache_ptr, const void* vcache_ptr,
+    const float* qscale_ptr, const float* kscale_ptr, const float* vscale_ptr,
+    const int* cu_seqlens_q_ptr, const int* block_ids_ptr, const int* seqlens_kv_ptr,
+    const uint8_t* block_mask_ptr, int num_batch, int total_seq_q, int max_seq_q, int num_head_q,
+    int num_head_kv, int num_dim, int num_kvcache_blocks, int block_size, int max_blocks,
+    int qscale_ld, int mask_mq, int mask_kb, int ldY, int ldQ, int64_t k_blk, int64_t k_tok,
+    int64_t k_head, int64_t v_blk, int64_t v_tok, int64_t v_head, cudaStream_t stream);
+int hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async(
+    void* y_ptr, const void* q_ptr, const void* kcache_ptr, const void* vcache_ptr,
+    const float* qscale_ptr, const float* kscale_ptr, const float* vscale_ptr,
+    const int* cu_seqlens_q_ptr, const int* block_ids_ptr, const int* seqlens_kv_ptr,
+    const uint8_t* block_mask_ptr, int num_batch, int total_seq_q, int max_seq_q, int num_head_q,
+    int num_head_kv, int num_dim, int num_kvcache_blocks, int block_size, int max_blocks,
+    int qscale_ld, int mask_mq, int mask_kb, int ldY, int ldQ, int64_t k_blk, int64_t k_tok,
+    int64_t k_head, int64_t v_blk, int64_t v_tok, int64_t v_head, int64_t ks_blk, int64_t ks_grp,
+    int64_t ks_head, cudaStream_t stream);
+
 /* ---- bring-up self test: one CTA, nk tcgen05.mma (kind::f8f6f4) with caller-supplied smem
  * images and descriptor fields; D[128, ncols] fp32 is copied out of TMEM. Used by tests to pin
  * the UMMA descriptor conventions the kernels rely on. */

@@ -177,7 +177,33 @@ def moe_pertensor_case(tag, T, K, H, I, E_total, size_ep, rank_ep, seed):
     print("wrote moe_pertensor", tag, gt.shape)
 
 
+def prefill_case(tag, k_per_token, seq, Hq, Hkv, skip, layout, seed):
+    from oracle import prefill as op
+    if k_per_token:
+        path = REF / "tests/test_attention_blocksparse_qkpertoken_perhead_vperhead_fp8.py"
+        name = "naive_attn_with_kvcache_qkpv_sparse_fixed_pscale"
+    else:
+        path = REF / "tests/test_attention_blocksparse_qpertoken_perhead_kvpertensor_fp8.py"
+        name = "naive_attn_with_kvcache_sparse_fixed_pscale"
+    ns = extract_many(path, {name})
+    ns["BSA_BLOCK"] = 128
+    B = 2
+    d = op.make_inputs([seq] * B, [seq] * B, Hq, Hkv, skip, k_per_token, seed=seed, layout=layout)
+    gt = ns[name](d["q"].reshape(B, seq, Hq, 128), d["kcache"], d["vcache"], d["qscale"], d["kscale"],
+                  d["vscale"], d["seqlens_kv"], d["block_ids"], block_mask=d["block_mask"], causal=True)
+    kvc = torch.stack([d["kcache"], d["vcache"]], dim=1).contiguous()
+    np.savez_compressed(
+        OUT / f"prefill_{tag}.npz", q=u8(d["q"]), kv=u8(kvc), qscale=d["qscale"].numpy(),
+        kscale=d["kscale"].numpy(), vscale=d["vscale"].numpy(), block_ids=d["block_ids"].numpy(),
+        mask=(d["block_mask"].numpy() if d["block_mask"] is not None else np.zeros(0, bool)),
+        out=gt.reshape(-1, Hq, 128).float().numpy(),
+        meta=np.array([B, seq, Hq, Hkv, int(k_per_token), 0 if layout == "nhd" else 1]))
+    print("wrote prefill", tag, gt.shape)
+
+
 if __name__ == "__main__":
+    prefill_case("kvpt", False, 384, 4, 1, 0.5, "nhd", 10086)
+    prefill_case("kpertoken", True, 320, 4, 2, 0.5, "hnd", 10086)
     moe_blockwise_case("a", 24, 4, 256, 128, 8, 2, 1, True, 41)
     moe_blockwise_case("b", 48, 8, 256, 256, 8, 1, 0, False, 7)
     moe_pertensor_case("a", 32, 4, 256, 128, 8, 1, 0, 5)
