@@ -21,8 +21,14 @@ def _run(hpc, d, kpt):
         c["block_ids"], c["seqlens_kv"], d["max_q"], quant_type=qt, block_mask=mask)
 
 
-def _check(my, gt, tag):
+def _check(my, gt, tag, allow_nan_rows=False):
     my, gt = my.float().cpu(), gt.float()
+    if allow_nan_rows:
+        # a Q tile without any active KV tile is NaN in the reference too (hpc/attention.py:274-277):
+        # the NaN rows must coincide, everything else is compared
+        assert torch.equal(torch.isnan(my), torch.isnan(gt)), f"{tag}: NaN pattern differs"
+        keep = ~torch.isnan(gt)
+        my, gt = my[keep], gt[keep]
     assert torch.isfinite(my).all(), f"{tag}: non-finite"
     err = (my - gt).abs()
     rel = err.norm() / gt.norm().clamp_min(1e-6)
@@ -54,7 +60,7 @@ def test_blocksparse_prefill_ragged_and_chunked(hpc, kpt):
     q_lens = [1, 130, 257, 64]
     kv_lens = [1, 130, 900, 1000]
     d = op.make_inputs(q_lens, kv_lens, 8, 2, 0.4, kpt, seed=3)
-    _check(_run(hpc, d, kpt), _oracle(d, kpt), f"ragged kpt={kpt}")
+    _check(_run(hpc, d, kpt), _oracle(d, kpt), f"ragged kpt={kpt}", allow_nan_rows=True)
     d = op.make_inputs(q_lens, kv_lens, 8, 2, None, kpt, seed=4, layout="hnd")
     _check(_run(hpc, d, kpt), _oracle(d, kpt), f"ragged dense kpt={kpt}")
 
