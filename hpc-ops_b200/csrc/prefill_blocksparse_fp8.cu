@@ -21,6 +21,7 @@
 //                smem, O tile TMEM -> fp32 register accumulator with rescale.
 // TMEM: S and O_tile double buffered (4 x 128 columns).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "host_utils.h"
@@ -368,44 +369,49 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       };
 
-      for (int i = 0; i < nact; i++) {
-        const int j = list[i];
-        const uint32_t buf = n & 1;
-        const uint32_t st = n % kStages;
-        mbar_wait(&s_full[buf], (n >> 1) & 1);
-        tc_fence_after();
-        const int key0 = j * kTile;
-        const bool need_mask = (key0 + kTile - 1 > tile_lim_min) || (key0 + kTile > k.seq_kv);
-        const float* ksr = ks_smem + st * 128;
-        // ---- pass 1: row max ----
+      // One KV tile of the online softmax. kMask is only needed on the causal diagonal / tail
+      // tiles; the unmasked instantiation is the hot path. P is produced directly as 256 * p
+      // (the +8 is folded into the exponent bias), so `lrun` is the row sum in units of 1/256 and
+      // the two factors cancel in the epilogue.
+      auto softmax_tile = [&](auto mask_tag, const int key0, const uint32_t buf, const float* ksr,
+                              float& alpha_out) {
+        constexpr bool kMask = decltype(mask_tag)::value;
+        const uint32_t s_addr = lane_addr + buf * 128;
+        // ---- pass 1: row max of the scaled scores ----
         float mx = -INFINITY;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; c++) {
           uint32_t sr[32];
-          tmem_ld_x32(lane_addr + buf * 128 + c * 32, sr);
+          tmem_ld_x32(s_addr + c * 32, sr);
           tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; e++) {
-            float v = __uint_as_float(sr[e]) * cq;
-            if constexpr (kKPerToken) v *= ksr[c * 32 + e];
-            if (need_mask) {
-              const int pos = key0 + c * 32 + e;
-              v = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v;
+          for (int e = 0; e < 32; e += 2) {
+            float v0 = __uint_as_float(sr[e]) * cq;
+            float v1 = __uint_as_float(sr[e + 1]) * cq;
+            if constexpr (kKPerToken) {
+              v0 *= ksr[c * 32 + e];
+              v1 *= ksr[c * 32 + e + 1];
             }
-            mx = fmaxf(mx, v);
+            if constexpr (kMask) {
+              const int pos = key0 + c * 32 + e;
+              v0 = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v0;
+              v1 = (pos + 1 > row_lim || pos + 1 >= k.seq_kv) ? -INFINITY : v1;
+            }
+            mx = fmaxf(mx, fmaxf(v0, v1));
           }
         }
         if (!row_ok) mx = -INFINITY;
         const float mnew = fmaxf(mrun, mx);
         const bool dead = (mnew == -INFINITY);
-        const float alpha = dead ? 1.f : exp2_approx(mrun - mnew);
-        // ---- pass 2: P = exp2(s - m) ; sum ; P*256 -> e4m3 -> swizzled smem row ----
+        alpha_out = dead ? 1.f : exp2_approx(mrun - mnew);
+        const float bias = dead ? -INFINITY : 8.f - mnew;
+        // ---- pass 2: 256 * exp2(s - m) -> e4m3 -> swizzled smem row; row sum ----
         float psum = 0.f;
         uint8_t* prow = p_smem + buf * kTileBytes + row * 128;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; c++) {
           uint32_t sr[32];
-          tmem_ld_x32(lane_addr + buf * 128 + c * 32, sr);
+          tmem_ld_x32(s_addr + c * 32, sr);
           tmem_wait_ld();
           uint32_t packed[8];
 #pragma unroll
@@ -414,15 +420,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int t = 0; t < 4; t++) {
               const int e = q4 * 4 + t;
-              float v = __uint_as_float(sr[e]) * cq;
-              if constexpr (kKPerToken) v *= ksr[c * 32 + e];
-              if (need_mask) {
+              float raw = __uint_as_float(sr[e]);
+              if constexpr (kKPerToken) raw *= ksr[c * 32 + e];
+              float x = fmaf(raw, cq, bias);
+              if constexpr (kMask) {
                 const int pos = key0 + c * 32 + e;
-                v = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v;
+                x = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : x;
               }
-              const float pe = dead ? 0.f : exp2_approx(v - mnew);
+              const float pe = exp2_approx(x);
               psum += pe;
-              e4[t] = pe * 256.f;
+              e4[t] = pe;
             }
             packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
           }
@@ -433,7 +440,24 @@ __global__ void __launch_bounds__(kThreads, 1)
               make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
         mrun = mnew;
-        lrun = lrun * alpha + psum;
+        lrun = lrun * alpha_out + psum;
+      };
+
+      for (int i = 0; i < nact; i++) {
+        const int j = list[i];
+        const uint32_t buf = n & 1;
+        const uint32_t st = n % kStages;
+        mbar_wait(&s_full[buf], (n >> 1) & 1);
+        tc_fence_after();
+        const int key0 = j * kTile;
+        const bool need_mask = (key0 + kTile - 1 > tile_lim_min) || (key0 + kTile > k.seq_kv);
+        const float* ksr = ks_smem + st * 128;
+        float alpha;
+        if (need_mask) {
+          softmax_tile(std::true_type{}, key0, buf, ksr, alpha);
+        } else {
+          softmax_tile(std::false_type{}, key0, buf, ksr, alpha);
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&p_full[buf]);
@@ -447,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
       // ---- epilogue: 1/sum, v scale, bf16 row out ----
       if (row_ok) {
-        const float vs = (kKPerToken ? __ldg(p.vscale + hkv) : p.vscale[0]) * (1.f / 256.f);
+        const float vs = kKPerToken ? __ldg(p.vscale + hkv) : p.vscale[0];  // (v/256)/(sum/256)
         // a row whose every visible tile was skipped has sum 0 -> NaN, as documented for the
         // reference (hpc/attention.py:274-277)
         const float inv = vs / lrun;
