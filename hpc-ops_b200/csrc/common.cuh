@@ -115,22 +115,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// suspend-time hint: a waiting thread sleeps in hardware (woken by the phase completion) instead of
+// re-issuing try_wait; polling instructions otherwise steal issue slots from the working warps
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 #ifndef B200_MBAR_SPIN_LIMIT
-#define B200_MBAR_SPIN_LIMIT (1u << 26)
+#define B200_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -321,6 +324,18 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
         "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
         "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+
+// Compiler-level anchor: values produced by an (asynchronous) tcgen05.ld may only be consumed after
+// tcgen05.wait::ld. Passing the registers through an empty volatile asm placed after the wait
+// keeps the compiler from scheduling their consumers above it (zero instructions emitted).
+__device__ __forceinline__ void tmem_anchor16(uint32_t* r) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                 "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ constexpr int kTile = 128;
 constexpr int kPage = 64;
 constexpr int kD = 128;
 constexpr int kTileBytes = kTile * kD;  // 16 KB fp8
-constexpr int kStages = 4;
+constexpr int kStages = 2;
 constexpr int kStageBytes = 2 * kTileBytes;
 constexpr int kThreads = 256;
 constexpr int kMaxKvTiles = 1024;  // seq_kv <= 128 K
@@ -94,22 +94,35 @@ __device__ __forceinline__ bool decode_work(const Params& p, int w, Work& k) {
   return true;
 }
 
+// Two CTAs are resident per SM (each 256 threads, ~102 KB smem, 256 TMEM columns): while one CTA's
+// softmax warpgroup works on a tile, the other CTA's MMAs and TMA loads run, which is what keeps
+// the tensor pipe and the MUFU busy at the same time. Inside a CTA S, P and O_tile are therefore
+// single buffered and the per-tile chain is QK -> softmax -> PV -> accumulate.
 template <bool kKPerToken>
 struct Smem {
   static constexpr int kOffStages = 0;
-  static constexpr int kOffQ = kStages * kStageBytes;            // 2 x 16 KB
-  static constexpr int kOffP = kOffQ + 2 * kTileBytes;           // 2 x 16 KB
-  static constexpr int kOffKs = kOffP + 2 * kTileBytes;          // kStages x 128 floats
-  static constexpr int kOffList = kOffKs + kStages * 128 * 4;    // 2 x (kMaxKvTiles + 8) int16
-  static constexpr int kListStride = kMaxKvTiles + 8;
-  static constexpr int kOffBar = kOffList + 2 * kListStride * 2;
-  static constexpr int kNumBars = 3 * kStages + 12;
+  static constexpr int kOffQ = kStages * kStageBytes;  // 16 KB
+  static constexpr int kOffP = kOffQ + kTileBytes;     // 16 KB
+  static constexpr int kOffKs = kOffP + kTileBytes;    // kStages x 128 floats
+  static constexpr int kOffList = kOffKs + kStages * 128 * 4;
+  static constexpr int kListStride = kMaxKvTiles + 8;  // int16 entries
+  static constexpr int kOffBar = kOffList + kListStride * 2;
+  static constexpr int kNumBars = 3 * kStages + 6;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmem + 64;
 };
 
+// Protocol (all mbarriers; "phase" = use-count parity):
+//   q_full      producer: item published (list + work id in smem, Q tile landed)
+//   q_empty     MMA thread (commit after the item's last QK) + 128 softmax threads (item finished)
+//   k_full/v_full[st], stage_empty[st]   KV ring (stage released by the commit after PV)
+//   s_full      commit after QK(n)             -> softmax
+//   p_full      128 softmax threads wrote P(n) -> MMA thread (also means S(n) has been read)
+//   o_full      commit after PV(n)             -> softmax
+// S(n+1) is only written after p_full(n); O(n+1) only after p_full(n+1), which each softmax
+// thread arrives on after it has read O(n); P(n+1) is written after o_full(n) (PV(n) finished).
 template <bool kKPerToken>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
     prefill_blocksparse_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                    const __grid_constant__ CUtensorMap tmap_k,
                                    const __grid_constant__ CUtensorMap tmap_v, const Params p) {
@@ -119,19 +132,19 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* q_smem = smem + L::kOffQ;
   uint8_t* p_smem = smem + L::kOffP;
   float* ks_smem = reinterpret_cast<float*>(smem + L::kOffKs);
-  int16_t* lists = reinterpret_cast<int16_t*>(smem + L::kOffList);
+  int16_t* list = reinterpret_cast<int16_t*>(smem + L::kOffList);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
+  int* s_work = reinterpret_cast<int*>(tmem_slot + 4);  // work id, number of active tiles
 
   uint64_t* k_full = bars;
   uint64_t* v_full = bars + kStages;
   uint64_t* stage_empty = bars + 2 * kStages;
-  uint64_t* q_full = bars + 3 * kStages;   // [2] work item published (Q landed + list written)
-  uint64_t* q_empty = q_full + 2;          // [2]
-  uint64_t* s_full = q_full + 4;           // [2]
-  uint64_t* p_full = q_full + 6;           // [2]
-  uint64_t* o_full = q_full + 8;           // [2]
-  uint64_t* list_full = q_full + 10;       // [2] producer lanes finished writing the list
+  uint64_t* q_full = bars + 3 * kStages;
+  uint64_t* q_empty = q_full + 1;
+  uint64_t* s_full = q_full + 2;
+  uint64_t* p_full = q_full + 3;
+  uint64_t* o_full = q_full + 4;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -146,18 +159,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&v_full[i], 1);
       mbar_init(&stage_empty[i], 1);
     }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1 + 128);  // MMA thread (commit) + softmax threads
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&list_full[i], 32);
-    }
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1 + 128);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -165,165 +175,147 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Every role walks the same sequence of work items. The producer claims them from the global
-  // counter and publishes {work id, active-tile count} + the tile list through smem (slot = item
-  // parity), guarded by q_full / q_empty.
-  int* s_work = reinterpret_cast<int*>(tmem_slot + 4);  // [2][2]: work id, number of active tiles
-
-  if (warp == 0) {
-    // =========================== producer ================================================
-    const uint64_t pol_kv = make_policy_evict_last();  // KV of a request is re-read by its q-heads
-    uint32_t n = 0;     // kv tile counter (ring)
-    uint32_t item = 0;  // item counter
-    while (true) {
-      int w = 0;
-      if (lane == 0) w = atomicAdd(p.work_counter, 1);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      Work k;
-      const bool alive = decode_work(p, w, k);
-      if (alive && k.rows == 0) continue;  // Q tile beyond this request
-      const uint32_t slot = item & 1;
-      mbar_wait(&q_empty[slot], ((item >> 1) & 1) ^ 1);
-      int16_t* list = lists + slot * L::kListStride;
-      int nact = 0;
-      if (alive) {
-        // ---- active tile list (ballot compaction, ascending j) ----
-        const int kb = p.block_mask ? p.mask_kb : k.num_tile_kv;
-        const int lim = k.num_tile_kv < kb ? k.num_tile_kv : kb;
-        const uint8_t* mrow =
-            p.block_mask
-                ? p.block_mask + ((static_cast<long long>(k.b) * p.num_head_q + k.hq) * p.mask_mq +
-                                  (k.mq < p.mask_mq ? k.mq : p.mask_mq - 1)) *
-                                     p.mask_kb
-                : nullptr;
-        for (int j0 = 0; j0 < lim; j0 += 32) {
-          const int j = j0 + lane;
-          const bool on = (j < lim) && (mrow == nullptr || mrow[j] != 0);
-          const unsigned m = __ballot_sync(0xffffffffu, on);
-          if (on) list[nact + __popc(m & ((1u << lane) - 1))] = static_cast<int16_t>(j);
-          nact += __popc(m);
-        }
-        if (p.block_mask && kb < k.num_tile_kv) {  // one unconditional tile past the mask width
-          if (lane == 0) list[nact] = static_cast<int16_t>(kb);
-          nact++;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        s_work[slot * 2] = alive ? w : -1;
-        s_work[slot * 2 + 1] = nact;
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    if (warp == 0) {
+      // =========================== producer ==============================================
+      const uint64_t pol_kv = make_policy_evict_last();  // KV of a request is re-read by its q-heads
+      uint32_t n = 0;     // kv tile counter (ring)
+      uint32_t item = 0;  // item counter
+      while (true) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.work_counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        Work k;
+        const bool alive = decode_work(p, w, k);
+        if (alive && k.rows == 0) continue;  // Q tile beyond this request
+        mbar_wait(q_empty, (item & 1) ^ 1);
+        int nact = 0;
         if (alive) {
-          mbar_arrive_expect_tx(&q_full[slot], kTileBytes);
-          tma_load_3d(q_smem + slot * kTileBytes, &tmap_q, &q_full[slot], 0, k.hq, k.q0);
-        } else {
-          mbar_arrive(&q_full[slot]);
-        }
-      }
-      __syncwarp();
-      item++;
-      if (!alive) break;
-      // ---- K/V tiles of the active list ----
-      const int hkv = k.hq / p.group;
-      const int nblk = (k.seq_kv + kPage - 1) / kPage;
-      const int* ids = p.block_ids + static_cast<long long>(k.b) * p.max_blocks;
-      const int kc1 = p.k_head_first ? hkv : 0, kc2 = p.k_head_first ? 0 : hkv;
-      const int vc1 = p.v_head_first ? hkv : 0, vc2 = p.v_head_first ? 0 : hkv;
-      for (int i0 = 0; i0 < nact; i0 += 16) {
-        // lanes 2t / 2t+1 fetch the two page ids of tile i0+t
-        const int ti = i0 + (lane >> 1);
-        int id = 0;
-        if (ti < nact) {
-          int blk = static_cast<int>(list[ti]) * 2 + (lane & 1);
-          blk = blk < nblk ? blk : nblk - 1;  // a missing 2nd page re-reads the 1st (keys masked)
-          id = __ldg(ids + blk);
-        }
-        const int cnt = (nact - i0) < 16 ? (nact - i0) : 16;
-        for (int t = 0; t < cnt; t++) {
-          const int id0 = __shfl_sync(0xffffffffu, id, 2 * t);
-          const int id1 = __shfl_sync(0xffffffffu, id, 2 * t + 1);
-          if (lane == 0) {
-            const uint32_t st = n % kStages;
-            mbar_wait(&stage_empty[st], ((n / kStages) & 1) ^ 1);
-            uint8_t* dst = stages + st * kStageBytes;
-            mbar_arrive_expect_tx(&k_full[st], kTileBytes + (kKPerToken ? 512 : 0));
-            tma_load_4d_hint(dst, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_kv);
-            tma_load_4d_hint(dst + kTileBytes / 2, &tmap_k, &k_full[st], 0, kc1, kc2, id1, pol_kv);
-            if constexpr (kKPerToken) {
-              // scales of token t of a page: kscale[page, t / 32, hkv, t % 32]
-              float* kd = ks_smem + st * 128;
-              const float* s0 = p.kscale + id0 * p.ks_stride_blk + hkv * p.ks_stride_head;
-              const float* s1 = p.kscale + id1 * p.ks_stride_blk + hkv * p.ks_stride_head;
-              bulk_load_1d(kd, s0, 128, &k_full[st]);
-              bulk_load_1d(kd + 32, s0 + p.ks_stride_grp, 128, &k_full[st]);
-              bulk_load_1d(kd + 64, s1, 128, &k_full[st]);
-              bulk_load_1d(kd + 96, s1 + p.ks_stride_grp, 128, &k_full[st]);
-            }
-            mbar_arrive_expect_tx(&v_full[st], kTileBytes);
-            tma_load_4d_hint(dst + kTileBytes, &tmap_v, &v_full[st], 0, vc1, vc2, id0, pol_kv);
-            tma_load_4d_hint(dst + kTileBytes + kTileBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2,
-                             id1, pol_kv);
+          // ---- active tile list (ballot compaction, ascending j) ----
+          const int kb = p.block_mask ? p.mask_kb : k.num_tile_kv;
+          const int lim = k.num_tile_kv < kb ? k.num_tile_kv : kb;
+          const uint8_t* mrow =
+              p.block_mask
+                  ? p.block_mask + ((static_cast<long long>(k.b) * p.num_head_q + k.hq) * p.mask_mq +
+                                    (k.mq < p.mask_mq ? k.mq : p.mask_mq - 1)) *
+                                       p.mask_kb
+                  : nullptr;
+          for (int j0 = 0; j0 < lim; j0 += 32) {
+            const int j = j0 + lane;
+            const bool on = (j < lim) && (mrow == nullptr || mrow[j] != 0);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) list[nact + __popc(m & ((1u << lane) - 1))] = static_cast<int16_t>(j);
+            nact += __popc(m);
           }
-          n++;
+          if (p.block_mask && kb < k.num_tile_kv) {  // one unconditional tile past the mask width
+            if (lane == 0) list[nact] = static_cast<int16_t>(kb);
+            nact++;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s_work[0] = alive ? w : -1;
+          s_work[1] = nact;
+          if (alive) {
+            mbar_arrive_expect_tx(q_full, kTileBytes);
+            tma_load_3d(q_smem, &tmap_q, q_full, 0, k.hq, k.q0);
+          } else {
+            mbar_arrive(q_full);
+          }
+        }
+        __syncwarp();
+        item++;
+        if (!alive) break;
+        // ---- K/V tiles of the active list ----
+        const int hkv = k.hq / p.group;
+        const int nblk = (k.seq_kv + kPage - 1) / kPage;
+        const int* ids = p.block_ids + static_cast<long long>(k.b) * p.max_blocks;
+        const int kc1 = p.k_head_first ? hkv : 0, kc2 = p.k_head_first ? 0 : hkv;
+        const int vc1 = p.v_head_first ? hkv : 0, vc2 = p.v_head_first ? 0 : hkv;
+        for (int i0 = 0; i0 < nact; i0 += 16) {
+          // lanes 2t / 2t+1 fetch the two page ids of tile i0+t
+          const int ti = i0 + (lane >> 1);
+          int id = 0;
+          if (ti < nact) {
+            int blk = static_cast<int>(list[ti]) * 2 + (lane & 1);
+            blk = blk < nblk ? blk : nblk - 1;  // a missing 2nd page re-reads the 1st (keys masked)
+            id = __ldg(ids + blk);
+          }
+          const int cnt = (nact - i0) < 16 ? (nact - i0) : 16;
+          for (int t = 0; t < cnt; t++) {
+            const int id0 = __shfl_sync(0xffffffffu, id, 2 * t);
+            const int id1 = __shfl_sync(0xffffffffu, id, 2 * t + 1);
+            if (lane == 0) {
+              const uint32_t st = n % kStages;
+              mbar_wait(&stage_empty[st], ((n / kStages) & 1) ^ 1);
+              uint8_t* dst = stages + st * kStageBytes;
+              mbar_arrive_expect_tx(&k_full[st], kTileBytes + (kKPerToken ? 512 : 0));
+              tma_load_4d_hint(dst, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_kv);
+              tma_load_4d_hint(dst + kTileBytes / 2, &tmap_k, &k_full[st], 0, kc1, kc2, id1, pol_kv);
+              if constexpr (kKPerToken) {
+                // scales of token t of a page: kscale[page, t / 32, hkv, t % 32]
+                float* kd = ks_smem + st * 128;
+                const float* s0 = p.kscale + id0 * p.ks_stride_blk + hkv * p.ks_stride_head;
+                const float* s1 = p.kscale + id1 * p.ks_stride_blk + hkv * p.ks_stride_head;
+                bulk_load_1d(kd, s0, 128, &k_full[st]);
+                bulk_load_1d(kd + 32, s0 + p.ks_stride_grp, 128, &k_full[st]);
+                bulk_load_1d(kd + 64, s1, 128, &k_full[st]);
+                bulk_load_1d(kd + 96, s1 + p.ks_stride_grp, 128, &k_full[st]);
+              }
+              mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+              tma_load_4d_hint(dst + kTileBytes, &tmap_v, &v_full[st], 0, vc1, vc2, id0, pol_kv);
+              tma_load_4d_hint(dst + kTileBytes + kTileBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2,
+                               id1, pol_kv);
+            }
+            n++;
+          }
         }
       }
-    }
-  } else if (warp == 1) {
-    // =========================== tcgen05 issuer (one thread) ==============================
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // =========================== tcgen05 issuer (one thread) ============================
       constexpr uint32_t idesc_qk = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 1);
       const uint64_t kdesc0 = make_smem_desc(smem_u32(stages), 16, 1024, kLayoutSW128);
       const uint64_t vdesc0 = make_smem_desc(smem_u32(stages) + kTileBytes, 16, 1024, kLayoutSW128);
-      const uint64_t qdesc0 = make_smem_desc(smem_u32(q_smem), 16, 1024, kLayoutSW128);
-      const uint64_t pdesc0 = make_smem_desc(smem_u32(p_smem), 16, 1024, kLayoutSW128);
-
-      auto issue_pv = [&](uint32_t m) {
-        const uint32_t st = m % kStages;
-        const uint32_t buf = m & 1;
-        mbar_wait(&p_full[buf], (m >> 1) & 1);
-        mbar_wait(&v_full[st], (m / kStages) & 1);
-        tc_fence_after();
-        const uint64_t ad = pdesc0 + static_cast<uint64_t>(buf * (kTileBytes >> 4));
-        const uint64_t bd = vdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
-        const uint32_t d = tmem_base + 256 + buf * 128;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
-          umma_f8(d, ad + k * 2, bd + k * (4096 >> 4), idesc_pv, k > 0);
-        }
-        umma_commit(&stage_empty[st]);
-        umma_commit(&o_full[buf]);
-      };
-
+      const uint64_t qdesc = make_smem_desc(smem_u32(q_smem), 16, 1024, kLayoutSW128);
+      const uint64_t pdesc = make_smem_desc(smem_u32(p_smem), 16, 1024, kLayoutSW128);
       uint32_t n = 0;
       uint32_t item = 0;
       while (true) {
-        const uint32_t slot = item & 1;
-        mbar_wait(&q_full[slot], (item >> 1) & 1);
-        const int w = s_work[slot * 2];
-        const int nact = s_work[slot * 2 + 1];
+        mbar_wait(q_full, item & 1);
+        const int w = s_work[0];
+        const int nact = s_work[1];
         if (w < 0) break;
-        const uint64_t ad = qdesc0 + static_cast<uint64_t>(slot * (kTileBytes >> 4));
         for (int i = 0; i < nact; i++) {
           const uint32_t st = n % kStages;
-          const uint32_t buf = n & 1;
+          const uint64_t so = static_cast<uint64_t>(st * (kStageBytes >> 4));
           mbar_wait(&k_full[st], (n / kStages) & 1);
+          if (n > 0) mbar_wait(p_full, (n - 1) & 1);  // S(n-1) has been read by every row
           tc_fence_after();
-          const uint64_t bd = kdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
-          const uint32_t d = tmem_base + buf * 128;
 #pragma unroll
-          for (int k = 0; k < 4; k++) umma_f8(d, ad + k * 2, bd + k * 2, idesc_qk, k > 0);
-          umma_commit(&s_full[buf]);
-          if (n > 0) issue_pv(n - 1);
+          for (int k = 0; k < 4; k++)
+            umma_f8(tmem_base, qdesc + k * 2, kdesc0 + so + k * 2, idesc_qk, k > 0);
+          umma_commit(s_full);
+          if (i == nact - 1) umma_commit(q_empty);  // Q tile / list reusable after this QK
+          mbar_wait(p_full, n & 1);
+          mbar_wait(&v_full[st], (n / kStages) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
+            umma_f8(tmem_base + 128, pdesc + k * 2, vdesc0 + so + k * (4096 >> 4), idesc_pv, k > 0);
+          }
+          umma_commit(&stage_empty[st]);
+          umma_commit(o_full);
           n++;
         }
-        // Q tile (and the list slot) may be overwritten once every QK of the item has completed
-        umma_commit(&q_empty[slot]);
+        if (nact == 0) umma_commit(q_empty);
         item++;
       }
-      if (n > 0) issue_pv(n - 1);
     }
-  } else if (warp >= 4) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // =========================== softmax / epilogue =======================================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row of the tile == TMEM lane
@@ -333,14 +325,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t n = 0;
     uint32_t item = 0;
     while (true) {
-      const uint32_t slot = item & 1;
-      mbar_wait(&q_full[slot], (item >> 1) & 1);
-      const int w = s_work[slot * 2];
-      const int nact = s_work[slot * 2 + 1];
+      mbar_wait(q_full, item & 1);
+      const int w = s_work[0];
+      const int nact = s_work[1];
       if (w < 0) break;
       Work k;
       decode_work(p, w, k);
-      const int16_t* list = lists + slot * L::kListStride;
       const int hkv = k.hq / p.group;
       const bool row_ok = row < k.rows;
       const float qs = row_ok ? __ldg(p.qscale + (static_cast<long long>(k.b) * p.num_head_q + k.hq) *
@@ -350,54 +340,54 @@ __global__ void __launch_bounds__(kThreads, 1)
       // kv positions visible to this row: pos <= row_lim and pos < seq_kv
       const int row_lim = k.seq_kv - k.seq_q + k.mq * kTile + row;
       const int tile_lim_min = k.seq_kv - k.seq_q + k.mq * kTile;  // row 0
-      float mrun = -INFINITY, lrun = 0.f, alpha_pend = 1.f;
+      float mrun = -INFINITY, lrun = 0.f;
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; i++) acc[i] = 0.f;
-
-      auto consume_o = [&](uint32_t m) {
-        const uint32_t buf = m & 1;
-        mbar_wait(&o_full[buf], (m >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          uint32_t o[32];
-          tmem_ld_x32(lane_addr + 256 + buf * 128 + c * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i++) acc[c * 32 + i] = acc[c * 32 + i] * alpha_pend + __uint_as_float(o[i]);
-        }
-      };
 
       // One KV tile of the online softmax. kMask is only needed on the causal diagonal / tail
       // tiles; the unmasked instantiation is the hot path. P is produced directly as 256 * p
       // (the +8 is folded into the exponent bias), so `lrun` is the row sum in units of 1/256 and
       // the two factors cancel in the epilogue.
-      auto softmax_tile = [&](auto mask_tag, const int key0, const uint32_t buf, const float* ksr,
-                              float& alpha_out) {
+      auto softmax_tile = [&](auto mask_tag, const int key0, const float* ksr, float& alpha_out) {
         constexpr bool kMask = decltype(mask_tag)::value;
-        const uint32_t s_addr = lane_addr + buf * 128;
+        // TMEM loads are issued one 16-column chunk ahead of the arithmetic (tcgen05.wait::ld
+        // waits for everything outstanding, so the wait sits after the compute of the previous
+        // chunk): with one softmax warp per SM sub-partition nothing else hides that latency.
         // ---- pass 1: row max of the scaled scores ----
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t sr[32];
-          tmem_ld_x32(s_addr + c * 32, sr);
-          tmem_wait_ld();
+        auto max16 = [&](const uint32_t* sr, const int c) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 16; e += 2) {
             float v0 = __uint_as_float(sr[e]) * cq;
             float v1 = __uint_as_float(sr[e + 1]) * cq;
             if constexpr (kKPerToken) {
-              v0 *= ksr[c * 32 + e];
-              v1 *= ksr[c * 32 + e + 1];
+              v0 *= ksr[c * 16 + e];
+              v1 *= ksr[c * 16 + e + 1];
             }
             if constexpr (kMask) {
-              const int pos = key0 + c * 32 + e;
+              const int pos = key0 + c * 16 + e;
               v0 = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v0;
               v1 = (pos + 1 > row_lim || pos + 1 >= k.seq_kv) ? -INFINITY : v1;
             }
             mx = fmaxf(mx, fmaxf(v0, v1));
+          }
+        };
+        {
+          uint32_t ra[16], rb[16];
+          tmem_ld_x16(lane_addr, ra);
+          tmem_wait_ld();
+          tmem_anchor16(ra);
+#pragma unroll 1
+          for (int c = 0; c < 8; c += 2) {
+            tmem_ld_x16(lane_addr + (c + 1) * 16, rb);
+            max16(ra, c);
+            tmem_wait_ld();
+            tmem_anchor16(rb);
+            if (c + 2 < 8) tmem_ld_x16(lane_addr + (c + 2) * 16, ra);
+            max16(rb, c + 1);
+            tmem_wait_ld();
+            tmem_anchor16(ra);
           }
         }
         if (!row_ok) mx = -INFINITY;
@@ -407,24 +397,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         const float bias = dead ? -INFINITY : 8.f - mnew;
         // ---- pass 2: 256 * exp2(s - m) -> e4m3 -> swizzled smem row; row sum ----
         float psum = 0.f;
-        uint8_t* prow = p_smem + buf * kTileBytes + row * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; c++) {
-          uint32_t sr[32];
-          tmem_ld_x32(s_addr + c * 32, sr);
-          tmem_wait_ld();
-          uint32_t packed[8];
+        uint8_t* prow = p_smem + row * 128;
+        auto exp16 = [&](const uint32_t* sr, const int c) {
+          uint32_t packed[4];
 #pragma unroll
-          for (int q4 = 0; q4 < 8; q4++) {
+          for (int q4 = 0; q4 < 4; q4++) {
             float e4[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
               const int e = q4 * 4 + t;
               float raw = __uint_as_float(sr[e]);
-              if constexpr (kKPerToken) raw *= ksr[c * 32 + e];
+              if constexpr (kKPerToken) raw *= ksr[c * 16 + e];
               float x = fmaf(raw, cq, bias);
               if constexpr (kMask) {
-                const int pos = key0 + c * 32 + e;
+                const int pos = key0 + c * 16 + e;
                 x = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : x;
               }
               const float pe = exp2_approx(x);
@@ -433,11 +419,26 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
           }
-          // 32 keys = two 16-B chunks (2c, 2c+1) of this row, 128B swizzle: chunk ^ (row & 7)
-          *reinterpret_cast<uint4*>(prow + (((2 * c) ^ (row & 7)) << 4)) =
+          // 16 keys = 16-B chunk c of this row, 128B swizzle: chunk ^ (row & 7)
+          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
               make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          *reinterpret_cast<uint4*>(prow + (((2 * c + 1) ^ (row & 7)) << 4)) =
-              make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        };
+        {
+          uint32_t ra[16], rb[16];
+          tmem_ld_x16(lane_addr, ra);
+          tmem_wait_ld();
+          tmem_anchor16(ra);
+#pragma unroll 1
+          for (int c = 0; c < 8; c += 2) {
+            tmem_ld_x16(lane_addr + (c + 1) * 16, rb);
+            exp16(ra, c);
+            tmem_wait_ld();
+            tmem_anchor16(rb);
+            if (c + 2 < 8) tmem_ld_x16(lane_addr + (c + 2) * 16, ra);
+            exp16(rb, c + 1);
+            tmem_wait_ld();
+            tmem_anchor16(ra);
+          }
         }
         mrun = mnew;
         lrun = lrun * alpha_out + psum;
@@ -445,29 +446,49 @@ __global__ void __launch_bounds__(kThreads, 1)
 
       for (int i = 0; i < nact; i++) {
         const int j = list[i];
-        const uint32_t buf = n & 1;
         const uint32_t st = n % kStages;
-        mbar_wait(&s_full[buf], (n >> 1) & 1);
+        mbar_wait(s_full, n & 1);
         tc_fence_after();
         const int key0 = j * kTile;
         const bool need_mask = (key0 + kTile - 1 > tile_lim_min) || (key0 + kTile > k.seq_kv);
         const float* ksr = ks_smem + st * 128;
         float alpha;
         if (need_mask) {
-          softmax_tile(std::true_type{}, key0, buf, ksr, alpha);
+          softmax_tile(std::true_type{}, key0, ksr, alpha);
         } else {
-          softmax_tile(std::false_type{}, key0, buf, ksr, alpha);
+          softmax_tile(std::false_type{}, key0, ksr, alpha);
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&p_full[buf]);
-
-        if (i > 0) consume_o(n - 1);
-        alpha_pend = alpha;
+        mbar_arrive(p_full);
+        // ---- O_tile(n) -> register accumulator ----
+        mbar_wait(o_full, n & 1);
+        tc_fence_after();
+        {
+          uint32_t oa[16], ob[16];
+          tmem_ld_x16(lane_addr + 128, oa);
+          tmem_wait_ld();
+          tmem_anchor16(oa);
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            tmem_ld_x16(lane_addr + 128 + (c + 1) * 16, ob);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+              acc[c * 16 + e] = acc[c * 16 + e] * alpha + __uint_as_float(oa[e]);
+            tmem_wait_ld();
+            tmem_anchor16(ob);
+            if (c + 2 < 8) tmem_ld_x16(lane_addr + 128 + (c + 2) * 16, oa);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+              acc[(c + 1) * 16 + e] = acc[(c + 1) * 16 + e] * alpha + __uint_as_float(ob[e]);
+            tmem_wait_ld();
+            tmem_anchor16(oa);
+          }
+        }
         n++;
       }
-      if (nact > 0) consume_o(n - 1);
-      mbar_arrive(&q_empty[slot]);  // done with the list / work slot
+      tc_fence_before();
+      mbar_arrive(q_empty);  // done with the list / work slot
 
       // ---- epilogue: 1/sum, v scale, bf16 row out ----
       if (row_ok) {
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace prefill
@@ -602,7 +623,7 @@ static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, cons
   p.v_head_first = vhf;
   p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(128.f);
 
-  const int grid = sm_count();
+  const int grid = 2 * sm_count();  // two resident CTAs per SM
   if (k_per_token) {
     auto kern = prefill::prefill_blocksparse_fp8_kernel<true>;
     static bool cfg = false;
