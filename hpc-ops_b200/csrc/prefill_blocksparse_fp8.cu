@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
-            umma_f8(tmem_base + 128, pdesc + k * 2, vdesc0 + so + k * (4096 >> 4), idesc_pv, k > 0);
+            umma_f8(tmem_base + 128, pdesc + k * 2, vdesc0 + so + k * (4096 >> 4), idesc_pv,
+                    (k > 0) || (i > 0));
           }
           umma_commit(&stage_empty[st]);
           umma_commit(o_full);
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");  // registers are no longer tight
     // =========================== softmax / epilogue =======================================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row of the tile == TMEM lane
@@ -340,177 +341,179 @@ __global__ void __launch_bounds__(kThreads, 2)
       // kv positions visible to this row: pos <= row_lim and pos < seq_kv
       const int row_lim = k.seq_kv - k.seq_q + k.mq * kTile + row;
       const int tile_lim_min = k.seq_kv - k.seq_q + k.mq * kTile;  // row 0
-      float mrun = -INFINITY, lrun = 0.f;
-      float acc[128];
-#pragma unroll
-      for (int i = 0; i < 128; i++) acc[i] = 0.f;
+      // Online softmax with a LAZY reference maximum. `mref` is the exponent reference of the row:
+      // P = 256 * 2^(s - mref) is produced in ONE pass over the tile while the tile maximum is
+      // tracked; only when some row of the warp would overflow e4m3 (s - mref > 0.75, i.e.
+      // P > ~430) -- or has not seen a key yet -- the warp takes the exact two-pass path, moves
+      // mref and rescales its rows of O in TMEM (tcgen05.ld / st). O therefore accumulates in
+      // TMEM across the tiles of an item (PV issues with accumulate = true) and is read once.
+      float mref = -INFINITY, lrun = 0.f;
+      uint8_t* prow = p_smem + row * 128;
 
-      // One KV tile of the online softmax. kMask is only needed on the causal diagonal / tail
-      // tiles; the unmasked instantiation is the hot path. P is produced directly as 256 * p
-      // (the +8 is folded into the exponent bias), so `lrun` is the row sum in units of 1/256 and
-      // the two factors cancel in the epilogue.
-      auto softmax_tile = [&](auto mask_tag, const int key0, const float* ksr, float& alpha_out) {
+      // x = raw * (ks) * cq + bias for one 16-column chunk; returns max(x), optionally emits P
+      auto chunk16 = [&](auto mask_tag, auto emit_tag, const uint32_t* sr, const int c,
+                         const int key0, const float* ksr, const float bias, float& xmax,
+                         float& psum) {
         constexpr bool kMask = decltype(mask_tag)::value;
-        // TMEM loads are issued one 16-column chunk ahead of the arithmetic (tcgen05.wait::ld
-        // waits for everything outstanding, so the wait sits after the compute of the previous
-        // chunk): with one softmax warp per SM sub-partition nothing else hides that latency.
-        // ---- pass 1: row max of the scaled scores ----
-        float mx = -INFINITY;
-        auto max16 = [&](const uint32_t* sr, const int c) {
+        constexpr bool kEmit = decltype(emit_tag)::value;
+        uint32_t packed[4];
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float v0 = __uint_as_float(sr[e]) * cq;
-            float v1 = __uint_as_float(sr[e + 1]) * cq;
-            if constexpr (kKPerToken) {
-              v0 *= ksr[c * 16 + e];
-              v1 *= ksr[c * 16 + e + 1];
-            }
+        for (int q4 = 0; q4 < 4; q4++) {
+          float e4[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int e = q4 * 4 + t;
+            float raw = __uint_as_float(sr[e]);
+            if constexpr (kKPerToken) raw *= ksr[c * 16 + e];
+            float x = fmaf(raw, cq, bias);
             if constexpr (kMask) {
               const int pos = key0 + c * 16 + e;
-              v0 = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v0;
-              v1 = (pos + 1 > row_lim || pos + 1 >= k.seq_kv) ? -INFINITY : v1;
+              x = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : x;
             }
-            mx = fmaxf(mx, fmaxf(v0, v1));
-          }
-        };
-        {
-          uint32_t ra[16], rb[16];
-          tmem_ld_x16(lane_addr, ra);
-          tmem_wait_ld();
-          tmem_anchor16(ra);
-#pragma unroll 1
-          for (int c = 0; c < 8; c += 2) {
-            tmem_ld_x16(lane_addr + (c + 1) * 16, rb);
-            max16(ra, c);
-            tmem_wait_ld();
-            tmem_anchor16(rb);
-            if (c + 2 < 8) tmem_ld_x16(lane_addr + (c + 2) * 16, ra);
-            max16(rb, c + 1);
-            tmem_wait_ld();
-            tmem_anchor16(ra);
-          }
-        }
-        if (!row_ok) mx = -INFINITY;
-        const float mnew = fmaxf(mrun, mx);
-        const bool dead = (mnew == -INFINITY);
-        alpha_out = dead ? 1.f : exp2_approx(mrun - mnew);
-        const float bias = dead ? -INFINITY : 8.f - mnew;
-        // ---- pass 2: 256 * exp2(s - m) -> e4m3 -> swizzled smem row; row sum ----
-        float psum = 0.f;
-        uint8_t* prow = p_smem + row * 128;
-        auto exp16 = [&](const uint32_t* sr, const int c) {
-          uint32_t packed[4];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; q4++) {
-            float e4[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-              const int e = q4 * 4 + t;
-              float raw = __uint_as_float(sr[e]);
-              if constexpr (kKPerToken) raw *= ksr[c * 16 + e];
-              float x = fmaf(raw, cq, bias);
-              if constexpr (kMask) {
-                const int pos = key0 + c * 16 + e;
-                x = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : x;
-              }
+            xmax = fmaxf(xmax, x);
+            if constexpr (kEmit) {
               const float pe = exp2_approx(x);
               psum += pe;
               e4[t] = pe;
             }
-            packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
           }
+          if constexpr (kEmit) packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
+        }
+        if constexpr (kEmit) {
           // 16 keys = 16-B chunk c of this row, 128B swizzle: chunk ^ (row & 7)
           *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
               make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        };
-        {
-          uint32_t ra[16], rb[16];
-          tmem_ld_x16(lane_addr, ra);
+        }
+      };
+      // one pass over the 128 columns of S (TMEM loads issued one chunk ahead of the arithmetic)
+      auto pass = [&](auto mask_tag, auto emit_tag, const int key0, const float* ksr,
+                      const float bias, float& xmax, float& psum) {
+        uint32_t ra[16], rb[16];
+        tmem_ld_x16(lane_addr, ra);
+        tmem_wait_ld();
+        tmem_anchor16(ra);
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_x16(lane_addr + (c + 1) * 16, rb);
+          chunk16(mask_tag, emit_tag, ra, c, key0, ksr, bias, xmax, psum);
+          tmem_wait_ld();
+          tmem_anchor16(rb);
+          if (c + 2 < 8) tmem_ld_x16(lane_addr + (c + 2) * 16, ra);
+          chunk16(mask_tag, emit_tag, rb, c + 1, key0, ksr, bias, xmax, psum);
           tmem_wait_ld();
           tmem_anchor16(ra);
+        }
+      };
+
+      auto softmax_tile = [&](auto mask_tag, const int i, const int key0, const float* ksr) {
+        float xmax = -INFINITY, psum = 0.f;
+        bool slow = (i == 0);
+        if (!slow) {
+          // fast path: exponent reference = mref of the previous tiles
+          const float bias = (mref == -INFINITY) ? -INFINITY : 8.f - mref;
+          pass(mask_tag, std::true_type{}, key0, ksr, bias, xmax, psum);
+          const bool mine = row_ok && (mref == -INFINITY || xmax > 8.75f);
+          slow = __any_sync(0xffffffffu, mine);
+          if (!slow) lrun += psum;
+        }
+        if (slow) {
+          // exact path: tile maximum first (bias 0 => xmax is the scaled score maximum)
+          float tmax = -INFINITY, dummy = 0.f;
+          pass(mask_tag, std::false_type{}, key0, ksr, 0.f, tmax, dummy);
+          if (!row_ok) tmax = -INFINITY;
+          const bool update = (mref == -INFINITY) || (tmax > mref + 0.75f);
+          const float mnew = update ? fmaxf(mref, tmax) : mref;
+          const bool dead = (mnew == -INFINITY);
+          const float alpha = (dead || mref == -INFINITY) ? (dead ? 1.f : 0.f) : exp2_approx(mref - mnew);
+          psum = 0.f;
+          float xm2 = -INFINITY;
+          pass(mask_tag, std::true_type{}, key0, ksr, dead ? -INFINITY : 8.f - mnew, xm2, psum);
+          lrun = lrun * alpha + psum;
+          mref = mnew;
+          if (i > 0) {
+            // rescale this warp's rows of the O accumulator (tiles < n are complete: o_full(n-1)
+            // was waited at the top of the iteration)
+            const bool any_scale = __any_sync(0xffffffffu, alpha != 1.f);
+            if (any_scale) {
 #pragma unroll 1
-          for (int c = 0; c < 8; c += 2) {
-            tmem_ld_x16(lane_addr + (c + 1) * 16, rb);
-            exp16(ra, c);
-            tmem_wait_ld();
-            tmem_anchor16(rb);
-            if (c + 2 < 8) tmem_ld_x16(lane_addr + (c + 2) * 16, ra);
-            exp16(rb, c + 1);
-            tmem_wait_ld();
-            tmem_anchor16(ra);
+              for (int c = 0; c < 8; c++) {
+                uint32_t o[16];
+                tmem_ld_x16(lane_addr + 128 + c * 16, o);
+                tmem_wait_ld();
+                tmem_anchor16(o);
+#pragma unroll
+                for (int e = 0; e < 16; e++) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st_x16(lane_addr + 128 + c * 16, o);
+              }
+              tmem_wait_st();
+            }
           }
         }
-        mrun = mnew;
-        lrun = lrun * alpha_out + psum;
       };
 
       for (int i = 0; i < nact; i++) {
         const int j = list[i];
         const uint32_t st = n % kStages;
         mbar_wait(s_full, n & 1);
+        if (i > 0) mbar_wait(o_full, (n - 1) & 1);  // PV(n-1) done (in-order pipe: already true)
         tc_fence_after();
         const int key0 = j * kTile;
         const bool need_mask = (key0 + kTile - 1 > tile_lim_min) || (key0 + kTile > k.seq_kv);
         const float* ksr = ks_smem + st * 128;
-        float alpha;
         if (need_mask) {
-          softmax_tile(std::true_type{}, key0, ksr, alpha);
+          softmax_tile(std::true_type{}, i, key0, ksr);
         } else {
-          softmax_tile(std::false_type{}, key0, ksr, alpha);
+          softmax_tile(std::false_type{}, i, key0, ksr);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(p_full);
-        // ---- O_tile(n) -> register accumulator ----
-        mbar_wait(o_full, n & 1);
-        tc_fence_after();
-        {
-          uint32_t oa[16], ob[16];
-          tmem_ld_x16(lane_addr + 128, oa);
-          tmem_wait_ld();
-          tmem_anchor16(oa);
-#pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            tmem_ld_x16(lane_addr + 128 + (c + 1) * 16, ob);
-#pragma unroll
-            for (int e = 0; e < 16; e++)
-              acc[c * 16 + e] = acc[c * 16 + e] * alpha + __uint_as_float(oa[e]);
-            tmem_wait_ld();
-            tmem_anchor16(ob);
-            if (c + 2 < 8) tmem_ld_x16(lane_addr + 128 + (c + 2) * 16, oa);
-#pragma unroll
-            for (int e = 0; e < 16; e++)
-              acc[(c + 1) * 16 + e] = acc[(c + 1) * 16 + e] * alpha + __uint_as_float(ob[e]);
-            tmem_wait_ld();
-            tmem_anchor16(oa);
-          }
-        }
         n++;
       }
-      tc_fence_before();
-      mbar_arrive(q_empty);  // done with the list / work slot
-
-      // ---- epilogue: 1/sum, v scale, bf16 row out ----
-      if (row_ok) {
+      mbar_arrive(q_empty);  // the list / work slot / Q tile may be refilled by the producer
+      // ---- epilogue: O / sum * vscale -> bf16 row ----
+      if (nact > 0) {
+        mbar_wait(o_full, (n - 1) & 1);
+        tc_fence_after();
+      }
+      {
         const float vs = kKPerToken ? __ldg(p.vscale + hkv) : p.vscale[0];  // (v/256)/(sum/256)
         // a row whose every visible tile was skipped has sum 0 -> NaN, as documented for the
         // reference (hpc/attention.py:274-277)
         const float inv = vs / lrun;
         __nv_bfloat16* dst = p.out + static_cast<long long>(k.q0 + row) * p.ld_out + k.hq * kD;
+#pragma unroll 1
+        for (int c = 0; c < 8; c++) {
+          uint32_t o[16];
+          if (nact > 0) {
+            tmem_ld_x16(lane_addr + 128 + c * 16, o);
+            tmem_wait_ld();
+            tmem_anchor16(o);
+          } else {
 #pragma unroll
-        for (int v8 = 0; v8 < 16; v8++) {
-          uint4 wv;
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[v8 * 8 + 0] * inv, acc[v8 * 8 + 1] * inv);
-          __nv_bfloat162 b1 = __floats2bfloat162_rn(acc[v8 * 8 + 2] * inv, acc[v8 * 8 + 3] * inv);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[v8 * 8 + 4] * inv, acc[v8 * 8 + 5] * inv);
-          __nv_bfloat162 b3 = __floats2bfloat162_rn(acc[v8 * 8 + 6] * inv, acc[v8 * 8 + 7] * inv);
-          wv.x = *reinterpret_cast<uint32_t*>(&b0);
-          wv.y = *reinterpret_cast<uint32_t*>(&b1);
-          wv.z = *reinterpret_cast<uint32_t*>(&b2);
-          wv.w = *reinterpret_cast<uint32_t*>(&b3);
-          *reinterpret_cast<uint4*>(dst + v8 * 8) = wv;
+            for (int e = 0; e < 16; e++) o[e] = 0u;
+          }
+          if (row_ok) {
+            uint4 w0, w1;
+            __nv_bfloat162 b[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+              b[e] = __floats2bfloat162_rn(__uint_as_float(o[2 * e]) * inv,
+                                           __uint_as_float(o[2 * e + 1]) * inv);
+            w0.x = *reinterpret_cast<uint32_t*>(&b[0]);
+            w0.y = *reinterpret_cast<uint32_t*>(&b[1]);
+            w0.z = *reinterpret_cast<uint32_t*>(&b[2]);
+            w0.w = *reinterpret_cast<uint32_t*>(&b[3]);
+            w1.x = *reinterpret_cast<uint32_t*>(&b[4]);
+            w1.y = *reinterpret_cast<uint32_t*>(&b[5]);
+            w1.z = *reinterpret_cast<uint32_t*>(&b[6]);
+            w1.w = *reinterpret_cast<uint32_t*>(&b[7]);
+            *reinterpret_cast<uint4*>(dst + c * 16) = w0;
+            *reinterpret_cast<uint4*>(dst + c * 16 + 8) = w1;
+          }
         }
       }
+      tc_fence_before();  // orders the O reads before this thread's next p_full arrive
       item++;
     }
   }
