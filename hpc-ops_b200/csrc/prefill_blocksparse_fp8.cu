@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 
       // x = raw * (ks) * cq + bias for one 16-column chunk; returns max(x), optionally emits P
       auto chunk16 = [&](auto mask_tag, auto emit_tag, const uint32_t* sr, const int c,
-                         const int key0, const float* ksr, const float bias, float& xmax,
-                         float& psum) {
+                         const int key0, const float* ksr, const float bias, float* xmax,
+                         float* psum) {  // 4 independent max / sum chains (ILP)
         constexpr bool kMask = decltype(mask_tag)::value;
         constexpr bool kEmit = decltype(emit_tag)::value;
         uint32_t packed[4];
@@ -370,10 +370,10 @@ __global__ void __launch_bounds__(kThreads, 2)
               const int pos = key0 + c * 16 + e;
               x = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : x;
             }
-            xmax = fmaxf(xmax, x);
+            xmax[t] = fmaxf(xmax[t], x);
             if constexpr (kEmit) {
               const float pe = exp2_approx(x);
-              psum += pe;
+              psum[t] += pe;
               e4[t] = pe;
             }
           }
@@ -387,7 +387,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       };
       // one pass over the 128 columns of S (TMEM loads issued one chunk ahead of the arithmetic)
       auto pass = [&](auto mask_tag, auto emit_tag, const int key0, const float* ksr,
-                      const float bias, float& xmax, float& psum) {
+                      const float bias, float& xmax_out, float& psum_out) {
+        float xmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float psum[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t ra[16], rb[16];
         tmem_ld_x16(lane_addr, ra);
         tmem_wait_ld();
@@ -403,6 +405,8 @@ __global__ void __launch_bounds__(kThreads, 2)
           tmem_wait_ld();
           tmem_anchor16(ra);
         }
+        xmax_out = fmaxf(xmax_out, fmaxf(fmaxf(xmax[0], xmax[1]), fmaxf(xmax[2], xmax[3])));
+        psum_out += (psum[0] + psum[1]) + (psum[2] + psum[3]);
       };
 
       auto softmax_tile = [&](auto mask_tag, const int i, const int key0, const float* ksr) {
