@@ -10,16 +10,20 @@
 //   active = { j < min(num_tile_kv, Kb) : mask[b, hq, mq, j] } U { Kb if Kb < num_tile_kv }
 // Items are handed out heaviest-first (largest mq first) by a global atomic counter.
 //
-// CTA = 256 threads:
-//   warp 0     : TMA producer (Q tile, K/V pages -> 4-stage ring of 32 KB, k scales when per-token),
-//                builds the active-tile list of each item with ballot compaction
-//   warp 1     : tcgen05 issuer. S[128 q, 128 keys] = Q . K^T (K-major A/B);
-//                O_tile[128 q, 128 d] = P . V with P K-major from smem and V MN-major exactly as it
-//                lies in the cache (no software transpose, unlike wgmma fp8: utils.cuh:461-521)
-//   warps 4-7  : softmax, one thread per query row (row max / sum are thread-local): TMEM -> regs,
-//                scale, causal/length mask, base-2 online softmax, P*256 -> e4m3 into 128B-swizzled
-//                smem, O tile TMEM -> fp32 register accumulator with rescale.
-// TMEM: S and O_tile double buffered (4 x 128 columns).
+// CTA = 256 threads, two CTAs resident per SM:
+//   warp 0     : TMA producer (Q tile, K pages -> 2-slot ring, V pages -> 2-slot ring, per-token k
+//                scales), builds the active-tile list of each item with ballot compaction
+//   warp 1     : tcgen05 issuer (one thread). S[128 q, 128 keys] = Q . K^T (K-major A/B);
+//                O[128 q, 128 d] += P . V with P K-major from smem and V MN-major exactly as it
+//                lies in the cache (no software transpose, unlike wgmma fp8: utils.cuh:461-521).
+//                QK(n+1) is issued as soon as the softmax threads hold S(n) in registers, i.e. it
+//                runs under softmax(n); PV(n) follows when P(n) is in smem.
+//   warps 4-7  : softmax, one thread per query row (row max / sum are thread-local): the whole S
+//                row (128 fp32) is pulled TMEM -> registers at once, then scale, causal/length
+//                mask, base-2 online softmax with a lazy reference maximum, P*256 -> e4m3 into
+//                128B-swizzled smem. O stays in TMEM across the tiles of an item (rare rescale by
+//                tcgen05.ld/st) and is read once by the epilogue.
+// TMEM: 256 columns per CTA (S at +0, O at +128).
 #include <cstdlib>
 #include <type_traits>
 
@@ -94,33 +98,35 @@ __device__ __forceinline__ bool decode_work(const Params& p, int w, Work& k) {
   return true;
 }
 
-// Two CTAs are resident per SM (each 256 threads, ~102 KB smem, 256 TMEM columns): while one CTA's
-// softmax warpgroup works on a tile, the other CTA's MMAs and TMA loads run, which is what keeps
-// the tensor pipe and the MUFU busy at the same time. Inside a CTA S, P and O_tile are therefore
-// single buffered and the per-tile chain is QK -> softmax -> PV -> accumulate.
+// Two CTAs are resident per SM (each 256 threads, ~103 KB smem, 256 TMEM columns): the second CTA
+// fills the issue slots and the tensor pipe while the first one waits on a barrier.
+constexpr int kKsBufs = 4;  // k-scale buffers: one more than the K ring needs (see producer)
 template <bool kKPerToken>
 struct Smem {
-  static constexpr int kOffStages = 0;
-  static constexpr int kOffQ = kStages * kStageBytes;  // 16 KB
-  static constexpr int kOffP = kOffQ + kTileBytes;     // 16 KB
-  static constexpr int kOffKs = kOffP + kTileBytes;    // kStages x 128 floats
-  static constexpr int kOffList = kOffKs + kStages * 128 * 4;
+  static constexpr int kOffK = 0;                           // kStages x 16 KB
+  static constexpr int kOffV = kOffK + kStages * kTileBytes;  // kStages x 16 KB
+  static constexpr int kOffQ = kOffV + kStages * kTileBytes;  // 16 KB
+  static constexpr int kOffP = kOffQ + kTileBytes;          // 16 KB
+  static constexpr int kOffKs = kOffP + kTileBytes;         // kKsBufs x 128 floats
+  static constexpr int kOffList = kOffKs + kKsBufs * 128 * 4;
   static constexpr int kListStride = kMaxKvTiles + 8;  // int16 entries
   static constexpr int kOffBar = kOffList + kListStride * 2;
-  static constexpr int kNumBars = 3 * kStages + 6;
+  static constexpr int kNumBars = 4 * kStages + 5;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmem + 64;
 };
 
-// Protocol (all mbarriers; "phase" = use-count parity):
+// Protocol (all mbarriers; "phase" = use-count parity), n = running KV-tile counter of the CTA:
 //   q_full      producer: item published (list + work id in smem, Q tile landed)
 //   q_empty     MMA thread (commit after the item's last QK) + 128 softmax threads (item finished)
-//   k_full/v_full[st], stage_empty[st]   KV ring (stage released by the commit after PV)
-//   s_full      commit after QK(n)             -> softmax
-//   p_full      128 softmax threads wrote P(n) -> MMA thread (also means S(n) has been read)
-//   o_full      commit after PV(n)             -> softmax
-// S(n+1) is only written after p_full(n); O(n+1) only after p_full(n+1), which each softmax
-// thread arrives on after it has read O(n); P(n+1) is written after o_full(n) (PV(n) finished).
+//   k_full/k_empty[slot]   K ring; the slot is released by the commit after QK(n)
+//   v_full/v_empty[slot]   V ring; released by the commit after PV(n). v_empty also tells the
+//                          softmax threads that PV(n) is complete (P buffer free, O consistent)
+//   s_full      commit after QK(n)                            -> softmax
+//   s_free      128 softmax threads hold S(n) in registers     -> MMA thread may issue QK(n+1)
+//   p_full      128 softmax threads wrote P(n) (and rescaled O) -> MMA thread issues PV(n)
+// The k-scale buffer of tile n+2 was last read by softmax(n-2), which every softmax thread
+// finished before arriving on s_free(n-1), which precedes QK(n) and so the release of K slot n%2.
 template <bool kKPerToken>
 __global__ void __launch_bounds__(kThreads, 2)
     prefill_blocksparse_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -128,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, 2)
                                    const __grid_constant__ CUtensorMap tmap_v, const Params p) {
   using L = Smem<kKPerToken>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* stages = smem + L::kOffStages;
+  uint8_t* k_smem = smem + L::kOffK;
+  uint8_t* v_smem = smem + L::kOffV;
   uint8_t* q_smem = smem + L::kOffQ;
   uint8_t* p_smem = smem + L::kOffP;
   float* ks_smem = reinterpret_cast<float*>(smem + L::kOffKs);
@@ -138,13 +145,14 @@ __global__ void __launch_bounds__(kThreads, 2)
   int* s_work = reinterpret_cast<int*>(tmem_slot + 4);  // work id, number of active tiles
 
   uint64_t* k_full = bars;
-  uint64_t* v_full = bars + kStages;
-  uint64_t* stage_empty = bars + 2 * kStages;
-  uint64_t* q_full = bars + 3 * kStages;
+  uint64_t* k_empty = bars + kStages;
+  uint64_t* v_full = bars + 2 * kStages;
+  uint64_t* v_empty = bars + 3 * kStages;
+  uint64_t* q_full = bars + 4 * kStages;
   uint64_t* q_empty = q_full + 1;
   uint64_t* s_full = q_full + 2;
-  uint64_t* p_full = q_full + 3;
-  uint64_t* o_full = q_full + 4;
+  uint64_t* s_free = q_full + 3;
+  uint64_t* p_full = q_full + 4;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -156,14 +164,15 @@ __global__ void __launch_bounds__(kThreads, 2)
     prefetch_tensormap(&tmap_v);
     for (int i = 0; i < kStages; i++) {
       mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&stage_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1 + 128);
     mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (warp == 0) {
       // =========================== producer ==============================================
       const uint64_t pol_kv = make_policy_evict_last();  // KV of a request is re-read by its q-heads
-      uint32_t n = 0;     // kv tile counter (ring)
+      uint32_t n = 0;     // kv tile counter (rings)
       uint32_t item = 0;  // item counter
       while (true) {
         int w = 0;
@@ -248,14 +257,15 @@ __global__ void __launch_bounds__(kThreads, 2)
             const int id1 = __shfl_sync(0xffffffffu, id, 2 * t + 1);
             if (lane == 0) {
               const uint32_t st = n % kStages;
-              mbar_wait(&stage_empty[st], ((n / kStages) & 1) ^ 1);
-              uint8_t* dst = stages + st * kStageBytes;
+              const uint32_t ph = ((n / kStages) & 1) ^ 1;
+              mbar_wait(&k_empty[st], ph);  // QK(n - 2) finished
+              uint8_t* kd8 = k_smem + st * kTileBytes;
               mbar_arrive_expect_tx(&k_full[st], kTileBytes + (kKPerToken ? 512 : 0));
-              tma_load_4d_hint(dst, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_kv);
-              tma_load_4d_hint(dst + kTileBytes / 2, &tmap_k, &k_full[st], 0, kc1, kc2, id1, pol_kv);
+              tma_load_4d_hint(kd8, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_kv);
+              tma_load_4d_hint(kd8 + kTileBytes / 2, &tmap_k, &k_full[st], 0, kc1, kc2, id1, pol_kv);
               if constexpr (kKPerToken) {
                 // scales of token t of a page: kscale[page, t / 32, hkv, t % 32]
-                float* kd = ks_smem + st * 128;
+                float* kd = ks_smem + (n % kKsBufs) * 128;
                 const float* s0 = p.kscale + id0 * p.ks_stride_blk + hkv * p.ks_stride_head;
                 const float* s1 = p.kscale + id1 * p.ks_stride_blk + hkv * p.ks_stride_head;
                 bulk_load_1d(kd, s0, 128, &k_full[st]);
@@ -263,10 +273,11 @@ __global__ void __launch_bounds__(kThreads, 2)
                 bulk_load_1d(kd + 64, s1, 128, &k_full[st]);
                 bulk_load_1d(kd + 96, s1 + p.ks_stride_grp, 128, &k_full[st]);
               }
+              mbar_wait(&v_empty[st], ph);  // PV(n - 2) finished
+              uint8_t* vd8 = v_smem + st * kTileBytes;
               mbar_arrive_expect_tx(&v_full[st], kTileBytes);
-              tma_load_4d_hint(dst + kTileBytes, &tmap_v, &v_full[st], 0, vc1, vc2, id0, pol_kv);
-              tma_load_4d_hint(dst + kTileBytes + kTileBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2,
-                               id1, pol_kv);
+              tma_load_4d_hint(vd8, &tmap_v, &v_full[st], 0, vc1, vc2, id0, pol_kv);
+              tma_load_4d_hint(vd8 + kTileBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2, id1, pol_kv);
             }
             n++;
           }
@@ -276,10 +287,23 @@ __global__ void __launch_bounds__(kThreads, 2)
       // =========================== tcgen05 issuer (one thread) ============================
       constexpr uint32_t idesc_qk = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 1);
-      const uint64_t kdesc0 = make_smem_desc(smem_u32(stages), 16, 1024, kLayoutSW128);
-      const uint64_t vdesc0 = make_smem_desc(smem_u32(stages) + kTileBytes, 16, 1024, kLayoutSW128);
+      const uint64_t kdesc0 = make_smem_desc(smem_u32(k_smem), 16, 1024, kLayoutSW128);
+      const uint64_t vdesc0 = make_smem_desc(smem_u32(v_smem), 16, 1024, kLayoutSW128);
       const uint64_t qdesc = make_smem_desc(smem_u32(q_smem), 16, 1024, kLayoutSW128);
       const uint64_t pdesc = make_smem_desc(smem_u32(p_smem), 16, 1024, kLayoutSW128);
+      // S(m) = Q . K(m)^T; needs K(m) in smem and S(m-1) drained into the softmax registers
+      auto issue_qk = [&](const uint32_t m, const bool last_of_item) {
+        const uint32_t st = m % kStages;
+        mbar_wait(&k_full[st], (m / kStages) & 1);
+        if (m > 0) mbar_wait(s_free, (m - 1) & 1);
+        tc_fence_after();
+        const uint64_t kd = kdesc0 + static_cast<uint64_t>(st * (kTileBytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_f8(tmem_base, qdesc + k * 2, kd + k * 2, idesc_qk, k > 0);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+        if (last_of_item) umma_commit(q_empty);  // Q tile / list reusable after this QK
+      };
       uint32_t n = 0;
       uint32_t item = 0;
       while (true) {
@@ -287,36 +311,32 @@ __global__ void __launch_bounds__(kThreads, 2)
         const int w = s_work[0];
         const int nact = s_work[1];
         if (w < 0) break;
-        for (int i = 0; i < nact; i++) {
-          const uint32_t st = n % kStages;
-          const uint64_t so = static_cast<uint64_t>(st * (kStageBytes >> 4));
-          mbar_wait(&k_full[st], (n / kStages) & 1);
-          if (n > 0) mbar_wait(p_full, (n - 1) & 1);  // S(n-1) has been read by every row
-          tc_fence_after();
+        if (nact == 0) {
+          umma_commit(q_empty);
+        } else {
+          issue_qk(n, nact == 1);
+          for (int i = 0; i < nact; i++) {
+            if (i + 1 < nact) issue_qk(n + 1, i + 2 == nact);  // runs under softmax(n)
+            const uint32_t st = n % kStages;
+            mbar_wait(&v_full[st], (n / kStages) & 1);
+            mbar_wait(p_full, n & 1);
+            tc_fence_after();
+            const uint64_t vd = vdesc0 + static_cast<uint64_t>(st * (kTileBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_f8(tmem_base, qdesc + k * 2, kdesc0 + so + k * 2, idesc_qk, k > 0);
-          umma_commit(s_full);
-          if (i == nact - 1) umma_commit(q_empty);  // Q tile / list reusable after this QK
-          mbar_wait(p_full, n & 1);
-          mbar_wait(&v_full[st], (n / kStages) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
-            umma_f8(tmem_base + 128, pdesc + k * 2, vdesc0 + so + k * (4096 >> 4), idesc_pv,
-                    (k > 0) || (i > 0));
+            for (int k = 0; k < 4; k++) {
+              // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
+              umma_f8(tmem_base + 128, pdesc + k * 2, vd + k * (4096 >> 4), idesc_pv,
+                      (k > 0) || (i > 0));
+            }
+            umma_commit(&v_empty[st]);
+            n++;
           }
-          umma_commit(&stage_empty[st]);
-          umma_commit(o_full);
-          n++;
         }
-        if (nact == 0) umma_commit(q_empty);
         item++;
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");  // registers are no longer tight
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // =========================== softmax / epilogue =======================================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row of the tile == TMEM lane
@@ -337,133 +357,124 @@ __global__ void __launch_bounds__(kThreads, 2)
       const float qs = row_ok ? __ldg(p.qscale + (static_cast<long long>(k.b) * p.num_head_q + k.hq) *
                                                       p.qscale_ld + k.mq * kTile + row)
                               : 0.f;
-      const float cq = qs * ks_tensor * p.softmax_scale_log2;
+      // > 0 so that a masked score (-inf) stays -inf after scaling (an all-zero q row has qs = 0,
+      // and then every raw score is 0 as well)
+      const float cq = fmaxf(qs * ks_tensor * p.softmax_scale_log2, 1e-30f);
       // kv positions visible to this row: pos <= row_lim and pos < seq_kv
       const int row_lim = k.seq_kv - k.seq_q + k.mq * kTile + row;
       const int tile_lim_min = k.seq_kv - k.seq_q + k.mq * kTile;  // row 0
-      // Online softmax with a LAZY reference maximum. `mref` is the exponent reference of the row:
-      // P = 256 * 2^(s - mref) is produced in ONE pass over the tile while the tile maximum is
-      // tracked; only when some row of the warp would overflow e4m3 (s - mref > 0.75, i.e.
-      // P > ~430) -- or has not seen a key yet -- the warp takes the exact two-pass path, moves
-      // mref and rescales its rows of O in TMEM (tcgen05.ld / st). O therefore accumulates in
-      // TMEM across the tiles of an item (PV issues with accumulate = true) and is read once.
+      // Online softmax with a LAZY reference maximum `mref` (log2 units): P = 256 * 2^(s - mref).
+      // mref only moves when the tile maximum exceeds it by more than 0.75 (P would pass ~430 and
+      // approach the e4m3 limit 448) or when the row has not seen a key yet; only then are the
+      // row's O values in TMEM rescaled. With causal / block-sparse attention that happens on the
+      // first tiles of an item and rarely afterwards.
       float mref = -INFINITY, lrun = 0.f;
       uint8_t* prow = p_smem + row * 128;
 
-      // x = raw * (ks) * cq + bias for one 16-column chunk; returns max(x), optionally emits P
-      auto chunk16 = [&](auto mask_tag, auto emit_tag, const uint32_t* sr, const int c,
-                         const int key0, const float* ksr, const float bias, float* xmax,
-                         float* psum) {  // 4 independent max / sum chains (ILP)
+      auto softmax_tile = [&](auto mask_tag, const int i, const int key0, const float* ksr) {
         constexpr bool kMask = decltype(mask_tag)::value;
-        constexpr bool kEmit = decltype(emit_tag)::value;
-        uint32_t packed[4];
+        // ---- S row -> registers; S is then free for QK(n+1) ----
+        uint32_t sr[128];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; q4++) {
-          float e4[4];
+        for (int c = 0; c < 4; c++) tmem_ld_x32(lane_addr + c * 32, sr + c * 32);
+        tmem_wait_ld();
 #pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const int e = q4 * 4 + t;
-            float raw = __uint_as_float(sr[e]);
-            if constexpr (kKPerToken) raw *= ksr[c * 16 + e];
-            float x = fmaf(raw, cq, bias);
-            if constexpr (kMask) {
-              const int pos = key0 + c * 16 + e;
-              x = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : x;
+        for (int c = 0; c < 8; c++) tmem_anchor16(sr + c * 16);
+        tc_fence_before();
+        mbar_arrive(s_free);
+        // ---- pass 1: dequantised (and masked) scores in place, row maximum ----
+        float vmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int e0 = 0; e0 < 128; e0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; t += 2) {
+            const int e = e0 + t;
+            v[t] = __uint_as_float(sr[e]);
+            v[t + 1] = __uint_as_float(sr[e + 1]);
+            if constexpr (kKPerToken) {
+              const float2 ks2 = *reinterpret_cast<const float2*>(ksr + e);
+              unpack_f2(fmul2(pack_f2(v[t], v[t + 1]), pack_f2(ks2.x, ks2.y)), v[t], v[t + 1]);
             }
-            xmax[t] = fmaxf(xmax[t], x);
-            if constexpr (kEmit) {
-              const float pe = exp2_approx(x);
-              psum[t] += pe;
-              e4[t] = pe;
+            if constexpr (kMask) {
+              const int pos = key0 + e;
+              v[t] = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v[t];
+              v[t + 1] = (pos + 1 > row_lim || pos + 1 >= k.seq_kv) ? -INFINITY : v[t + 1];
+            }
+            if constexpr (kKPerToken || kMask) {
+              sr[e] = __float_as_uint(v[t]);
+              sr[e + 1] = __float_as_uint(v[t + 1]);
             }
           }
-          if constexpr (kEmit) packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
+#pragma unroll
+          for (int t = 0; t < 4; t++) vmax[t] = fmaxf(vmax[t], fmaxf(v[t], v[t + 4]));
         }
-        if constexpr (kEmit) {
+        float tmax = fmaxf(fmaxf(vmax[0], vmax[1]), fmaxf(vmax[2], vmax[3])) * cq;
+        if (!row_ok) tmax = -INFINITY;
+        const bool update = (mref == -INFINITY) || (tmax > mref + 0.75f);
+        const float mnew = update ? fmaxf(mref, tmax) : mref;
+        const bool dead = (mnew == -INFINITY);
+        const float alpha =
+            (dead || mref == -INFINITY) ? (dead ? 1.f : 0.f) : exp2_approx(mref - mnew);
+        mref = mnew;
+        if (i > 0) {
+          // PV(n-1) complete: the P buffer may be overwritten and O is consistent
+          mbar_wait(&v_empty[(n - 1) % kStages], ((n - 1) / kStages) & 1);
+          const bool any_scale = __any_sync(0xffffffffu, alpha != 1.f);
+          if (any_scale) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+              uint32_t o[16];
+              tmem_ld_x16(lane_addr + 128 + c * 16, o);
+              tmem_wait_ld();
+              tmem_anchor16(o);
+#pragma unroll
+              for (int e = 0; e < 16; e++) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_x16(lane_addr + 128 + c * 16, o);
+            }
+            tmem_wait_st();
+          }
+        }
+        // ---- pass 2: P = 256 * 2^(s - mref) -> e4m3, row sum ----
+        const uint64_t bias2 = dead ? pack_f2(-INFINITY, -INFINITY) : pack_f2(8.f - mnew, 8.f - mnew);
+        const uint64_t cq2 = pack_f2(cq, cq);
+        uint64_t psum2[2] = {0ull, 0ull};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; q4++) {
+            float e4[4];
+#pragma unroll
+            for (int t = 0; t < 4; t += 2) {
+              const int e = c * 16 + q4 * 4 + t;
+              float x0, x1;
+              unpack_f2(ffma2(pack_f2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), cq2, bias2),
+                        x0, x1);
+              e4[t] = exp2_approx(x0);
+              e4[t + 1] = exp2_approx(x1);
+              psum2[t >> 1] = fadd2(psum2[t >> 1], pack_f2(e4[t], e4[t + 1]));
+            }
+            packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
+          }
           // 16 keys = 16-B chunk c of this row, 128B swizzle: chunk ^ (row & 7)
           *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
               make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-      };
-      // one pass over the 128 columns of S (TMEM loads issued one chunk ahead of the arithmetic)
-      auto pass = [&](auto mask_tag, auto emit_tag, const int key0, const float* ksr,
-                      const float bias, float& xmax_out, float& psum_out) {
-        float xmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        float psum[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t ra[16], rb[16];
-        tmem_ld_x16(lane_addr, ra);
-        tmem_wait_ld();
-        tmem_anchor16(ra);
-#pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld_x16(lane_addr + (c + 1) * 16, rb);
-          chunk16(mask_tag, emit_tag, ra, c, key0, ksr, bias, xmax, psum);
-          tmem_wait_ld();
-          tmem_anchor16(rb);
-          if (c + 2 < 8) tmem_ld_x16(lane_addr + (c + 2) * 16, ra);
-          chunk16(mask_tag, emit_tag, rb, c + 1, key0, ksr, bias, xmax, psum);
-          tmem_wait_ld();
-          tmem_anchor16(ra);
-        }
-        xmax_out = fmaxf(xmax_out, fmaxf(fmaxf(xmax[0], xmax[1]), fmaxf(xmax[2], xmax[3])));
-        psum_out += (psum[0] + psum[1]) + (psum[2] + psum[3]);
-      };
-
-      auto softmax_tile = [&](auto mask_tag, const int i, const int key0, const float* ksr) {
-        float xmax = -INFINITY, psum = 0.f;
-        bool slow = (i == 0);
-        if (!slow) {
-          // fast path: exponent reference = mref of the previous tiles
-          const float bias = (mref == -INFINITY) ? -INFINITY : 8.f - mref;
-          pass(mask_tag, std::true_type{}, key0, ksr, bias, xmax, psum);
-          const bool mine = row_ok && (mref == -INFINITY || xmax > 8.75f);
-          slow = __any_sync(0xffffffffu, mine);
-          if (!slow) lrun += psum;
-        }
-        if (slow) {
-          // exact path: tile maximum first (bias 0 => xmax is the scaled score maximum)
-          float tmax = -INFINITY, dummy = 0.f;
-          pass(mask_tag, std::false_type{}, key0, ksr, 0.f, tmax, dummy);
-          if (!row_ok) tmax = -INFINITY;
-          const bool update = (mref == -INFINITY) || (tmax > mref + 0.75f);
-          const float mnew = update ? fmaxf(mref, tmax) : mref;
-          const bool dead = (mnew == -INFINITY);
-          const float alpha = (dead || mref == -INFINITY) ? (dead ? 1.f : 0.f) : exp2_approx(mref - mnew);
-          psum = 0.f;
-          float xm2 = -INFINITY;
-          pass(mask_tag, std::true_type{}, key0, ksr, dead ? -INFINITY : 8.f - mnew, xm2, psum);
-          lrun = lrun * alpha + psum;
-          mref = mnew;
-          if (i > 0) {
-            // rescale this warp's rows of the O accumulator (tiles < n are complete: o_full(n-1)
-            // was waited at the top of the iteration)
-            const bool any_scale = __any_sync(0xffffffffu, alpha != 1.f);
-            if (any_scale) {
-#pragma unroll 1
-              for (int c = 0; c < 8; c++) {
-                uint32_t o[16];
-                tmem_ld_x16(lane_addr + 128 + c * 16, o);
-                tmem_wait_ld();
-                tmem_anchor16(o);
-#pragma unroll
-                for (int e = 0; e < 16; e++) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                tmem_st_x16(lane_addr + 128 + c * 16, o);
-              }
-              tmem_wait_st();
-            }
-          }
-        }
+        float s0, s1, s2, s3;
+        unpack_f2(psum2[0], s0, s1);
+        unpack_f2(psum2[1], s2, s3);
+        lrun = lrun * alpha + ((s0 + s1) + (s2 + s3));
       };
 
       for (int i = 0; i < nact; i++) {
         const int j = list[i];
-        const uint32_t st = n % kStages;
         mbar_wait(s_full, n & 1);
-        if (i > 0) mbar_wait(o_full, (n - 1) & 1);  // PV(n-1) done (in-order pipe: already true)
         tc_fence_after();
         const int key0 = j * kTile;
         const bool need_mask = (key0 + kTile - 1 > tile_lim_min) || (key0 + kTile > k.seq_kv);
-        const float* ksr = ks_smem + st * 128;
+        const float* ksr = ks_smem + (n % kKsBufs) * 128;
         if (need_mask) {
           softmax_tile(std::true_type{}, i, key0, ksr);
         } else {
@@ -474,10 +485,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         mbar_arrive(p_full);
         n++;
       }
-      mbar_arrive(q_empty);  // the list / work slot / Q tile may be refilled by the producer
+      mbar_arrive(q_empty);  // the list / work slot may be refilled by the producer
       // ---- epilogue: O / sum * vscale -> bf16 row ----
       if (nact > 0) {
-        mbar_wait(o_full, (n - 1) & 1);
+        mbar_wait(&v_empty[(n - 1) % kStages], ((n - 1) / kStages) & 1);  // last PV of the item
         tc_fence_after();
       }
       {
