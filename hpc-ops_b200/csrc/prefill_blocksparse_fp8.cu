@@ -127,7 +127,30 @@ struct Smem {
 //   p_full      128 softmax threads wrote P(n) (and rescaled O) -> MMA thread issues PV(n)
 // The k-scale buffer of tile n+2 was last read by softmax(n-2), which every softmax thread
 // finished before arriving on s_free(n-1), which precedes QK(n) and so the release of K slot n%2.
-template <bool kKPerToken>
+// 2^x for a pair of scores on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial on
+// [-0.5, 0.5], relative error 7.5e-5): the MUFU unit (4 lanes per scheduler) is the busiest pipe of
+// the softmax pass, so a fixed share of the exponentials is computed this way instead.
+__device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack_f2(x2, x0, x1);
+  x0 = fmaxf(x0, -120.f);  // keeps 2^n a normal number; P below 2^-10 rounds to 0 anyway
+  x1 = fmaxf(x1, -120.f);
+  const uint64_t x = pack_f2(x0, x1);
+  const uint64_t t = fadd2(x, pack_f2(12582912.f, 12582912.f));  // 1.5 * 2^23: low bits = round(x)
+  const uint64_t r = fadd2(t, pack_f2(-12582912.f, -12582912.f));
+  const uint64_t f = ffma2(r, pack_f2(-1.f, -1.f), x);
+  uint64_t q = ffma2(f, pack_f2(0.0551716685f, 0.0551716685f), pack_f2(0.2426111251f, 0.2426111251f));
+  q = ffma2(q, f, pack_f2(0.6932609677f, 0.6932609677f));
+  q = ffma2(q, f, pack_f2(0.9999280572f, 0.9999280572f));
+  float q0, q1, t0, t1;
+  unpack_f2(q, q0, q1);
+  unpack_f2(t, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+// kPoly: exponentials per group of 8 scores that take the polynomial path (0, 2 or 4)
+template <bool kKPerToken, int kPoly>
 __global__ void __launch_bounds__(kThreads, 2)
     prefill_blocksparse_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                    const __grid_constant__ CUtensorMap tmap_k,
@@ -449,11 +472,17 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
             for (int t = 0; t < 4; t += 2) {
               const int e = c * 16 + q4 * 4 + t;
-              float x0, x1;
-              unpack_f2(ffma2(pack_f2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), cq2, bias2),
-                        x0, x1);
-              e4[t] = exp2_approx(x0);
-              e4[t + 1] = exp2_approx(x1);
+              const uint64_t x2 =
+                  ffma2(pack_f2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), cq2, bias2);
+              const bool poly = (t == 2) && (kPoly == 4 || (kPoly == 2 && (q4 & 1)));
+              if (poly) {
+                exp2_poly_pair(x2, e4[t], e4[t + 1]);
+              } else {
+                float x0, x1;
+                unpack_f2(x2, x0, x1);
+                e4[t] = exp2_approx(x0);
+                e4[t + 1] = exp2_approx(x1);
+              }
               psum2[t >> 1] = fadd2(psum2[t >> 1], pack_f2(e4[t], e4[t + 1]));
             }
             packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
@@ -542,6 +571,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 }  // namespace b200
 
 using namespace b200;  // NOLINT
+
+constexpr int kDefaultPoly = 2;
 
 static int encode_cache_map(CUtensorMap* tm, const void* base, int heads, int num_blocks,
                             int64_t blk_stride, int64_t tok_stride, int64_t head_stride,
@@ -642,25 +673,29 @@ static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, cons
   p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(128.f);
 
   const int grid = 2 * sm_count();  // two resident CTAs per SM
+  // share of exponentials on the FMA pipe: HPC_B200_PREFILL_POLY = 0 | 2 | 4 (per 8 scores)
+  static const int poly = [] {
+    const char* e = std::getenv("HPC_B200_PREFILL_POLY");
+    const int v = e ? std::atoi(e) : kDefaultPoly;
+    return (v == 0 || v == 2 || v == 4) ? v : kDefaultPoly;
+  }();
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, prefill::Params);
+  KernelFn kern;
+  int smem_bytes;
   if (k_per_token) {
-    auto kern = prefill::prefill_blocksparse_fp8_kernel<true>;
-    static bool cfg = false;
-    if (!cfg) {
-      HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          prefill::Smem<true>::kTotal));
-      cfg = true;
-    }
-    kern<<<grid, prefill::kThreads, prefill::Smem<true>::kTotal, stream>>>(tq, tk, tv, p);
+    smem_bytes = prefill::Smem<true>::kTotal;
+    kern = poly == 4   ? prefill::prefill_blocksparse_fp8_kernel<true, 4>
+           : poly == 2 ? prefill::prefill_blocksparse_fp8_kernel<true, 2>
+                       : prefill::prefill_blocksparse_fp8_kernel<true, 0>;
   } else {
-    auto kern = prefill::prefill_blocksparse_fp8_kernel<false>;
-    static bool cfg = false;
-    if (!cfg) {
-      HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          prefill::Smem<false>::kTotal));
-      cfg = true;
-    }
-    kern<<<grid, prefill::kThreads, prefill::Smem<false>::kTotal, stream>>>(tq, tk, tv, p);
+    smem_bytes = prefill::Smem<false>::kTotal;
+    kern = poly == 4   ? prefill::prefill_blocksparse_fp8_kernel<false, 4>
+           : poly == 2 ? prefill::prefill_blocksparse_fp8_kernel<false, 2>
+                       : prefill::prefill_blocksparse_fp8_kernel<false, 0>;
   }
+  HPC_CUDA_CHECK(cudaFuncSetAttribute(reinterpret_cast<const void*>(kern),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  kern<<<grid, prefill::kThreads, smem_bytes, stream>>>(tq, tk, tv, p);
   HPC_CUDA_CHECK(cudaGetLastError());
   return HPC_OK;
 }
