@@ -38,10 +38,8 @@ constexpr int kPage = 64;
 constexpr int kD = 128;
 constexpr int kTileBytes = kTile * kD;  // 16 KB fp8
 constexpr int kStages = 2;
-constexpr int kStageBytes = 2 * kTileBytes;
 constexpr int kThreads = 256;
 constexpr int kMaxKvTiles = 1024;  // seq_kv <= 128 K
-constexpr int kSoftmaxBar = 1;
 
 struct Params {
   const int* cu_seqlens_q;

@@ -25,20 +25,16 @@ def _gemm_bf16xfp32_impl(x, w_high, w_low, scale, use_fp32_output, use_splitk, s
     _require(n % 64 == 0, "n must to be divided by 64.")
     _require(tuple(w_low.shape) == tuple(w_high.shape) and w_high.size(1) == k, "weight shape mismatch")
     split_k = _lib.hpc_gemm_bf16xfp32_select_splitk(m, n, k, int(bool(use_splitk)))
-    split_y = None
-    flag_ld = 0
-    if split_k > 1:
-        split_y = torch.empty((split_k, m, n), dtype=torch.float32, device=x.device)
-        if split_flag is None:
-            split_flag = torch.zeros(((m + 127) // 128, (n + 63) // 64), dtype=torch.int32,
-                                     device=x.device)
+    # The k-splits reduce through cluster shared memory: no `split_y` scratch (reference
+    # entry.cc:116-129) is allocated and `split_flag` is validated but never written.
+    if split_flag is not None:
         _require(split_flag.dtype == torch.int32 and split_flag.is_cuda, "split_flag must be cuda int32")
-        flag_ld = split_flag.stride(0)
     y = torch.empty((m, n), dtype=torch.float32 if use_fp32_output else torch.bfloat16,
                     device=x.device)
     _check_rc(_lib.hpc_gemm_bf16xfp32_async(
-        _ptr(y), _ptr(split_y), _ptr(split_flag) if split_k > 1 else None, _ptr(x), _ptr(w_high),
-        _ptr(w_low), m, n, k, float(scale), int(bool(use_fp32_output)), split_k, 128, 1, flag_ld,
+        _ptr(y), None, _ptr(split_flag), _ptr(x), _ptr(w_high),
+        _ptr(w_low), m, n, k, float(scale), int(bool(use_fp32_output)), split_k, 128, 1,
+        split_flag.stride(0) if split_flag is not None else 0,
         _stream_of(x)), "gemm_bf16xfp32")
     return y
 

@@ -210,10 +210,11 @@ int hpc_fuse_allreduce_rmsnorm_low_latency_async(
 /* ---- BF16 x "FP32" route GEMM ---------------------------------------------------------------------
  * replaces reference src/gemm/gemm.h:12-15 (gemm_bf16xfp32_async):
  *   Y[m, n] = X . W_high^T + scale * (X . W_low^T), fp32 accumulate, bf16 or fp32 output.
- * split_k > 1 needs split_y f32 [split_k, m, n] and a zeroed int32 split_flag (left zeroed);
- * flag_ld = row stride of split_flag in ints (0 = dense). tile_m / k_warpgroup_n: sm_90 tile knobs
- * of the reference signature, accepted and ignored. hpc_gemm_bf16xfp32_select_splitk is the
- * heuristic the host uses to size split_y (role of reference src/gemm/sm90/entry.cc:25-84).
+ * split_k in {1, 2, 4, 8}: the k-splits of an output tile run as one thread-block cluster and
+ * reduce through distributed shared memory, so the reference's global workspaces split_y /
+ * split_flag / flag_ld (and its sm_90 tile knobs tile_m / k_warpgroup_n) are accepted and ignored;
+ * split_flag is never written and therefore stays zeroed. hpc_gemm_bf16xfp32_select_splitk is
+ * the host heuristic (role of reference src/gemm/sm90/entry.cc:25-84).
  */
 int hpc_gemm_bf16xfp32_select_splitk(int m, int n, int k, int use_splitk);
 int hpc_gemm_bf16xfp32_async(void* y_ptr, void* split_y_ptr, void* split_flag_ptr,
