@@ -244,17 +244,63 @@ static int pick_tile_n(int n) {
 
 using namespace b200;  // NOLINT
 
-// Split-K chosen for an (m, n, k) problem = cluster size along z (1, 2, 4 or 8).
+static constexpr int kSmemBytes = rgemm::kStageRegion + 256;
+
+static int configure_kernel() {
+  static bool configured = false;
+  if (!configured) {
+    HPC_CUDA_CHECK(cudaFuncSetAttribute(rgemm::gemm_bf16xfp32_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  return HPC_OK;
+}
+
+// Clusters of `split` CTAs (one CTA per SM, ~192 KB smem each) that can be resident at once. A
+// cluster must sit inside one GPC, so this is less than SMs / split for the larger sizes.
+static int max_resident_clusters(int split) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cache[split] > 0) return cache[split];
+  int n = 0;
+  if (configure_kernel() == HPC_OK) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, split);
+    cfg.blockDim = dim3(rgemm::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = split;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, rgemm::gemm_bf16xfp32_kernel, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      n = 0;
+    }
+  }
+  if (n <= 0) {  // no device / query failed: assume 148 SMs, 7/8 usable by clusters
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    n = split == 1 ? sms : (sms * 7 / 8) / split;
+  }
+  cache[split] = n;
+  return n;
+}
+
+// Split-K chosen for an (m, n, k) problem = cluster size along z (1, 2, 4 or 8): the largest
+// split whose clusters are all co-resident (a second wave would double the time of this
+// latency-bound op) and that leaves every CTA at least two k-steps.
 // Mirrors the role of reference src/gemm/sm90/entry.cc:25-84 (select_config).
 extern "C" int hpc_gemm_bf16xfp32_select_splitk(int m, int n, int k, int use_splitk) {
   if (!use_splitk || m <= 0 || n <= 0) return 1;
   const int tile_n = rgemm::pick_tile_n(n);
   const int tiles = ((m + rgemm::kBM - 1) / rgemm::kBM) * (n / tile_n);
   const int ksteps = (k + rgemm::kBK - 1) / rgemm::kBK;
-  int sms = sm_count();
-  if (sms <= 0) sms = 148;
   int split = 1;
-  while (split < 8 && tiles * split * 2 <= sms && ksteps / (split * 2) >= 2) split *= 2;
+  for (int s = 2; s <= 8; s *= 2) {
+    if (tiles <= max_resident_clusters(s) && ksteps / s >= 2) split = s;
+  }
   return split;
 }
 
@@ -309,13 +355,8 @@ extern "C" int hpc_gemm_bf16xfp32_async(void* y_ptr, void* split_y_ptr, void* sp
   const int stage_bytes = rgemm::kBM * rgemm::kBK * 2 + 2 * tile_n * rgemm::kBK * 2;
   p.stages = rgemm::kStageRegion / stage_bytes;
   if (p.stages > rgemm::kMaxStages) p.stages = rgemm::kMaxStages;
-  const int smem = rgemm::kStageRegion + 256;
-  static bool configured = false;
-  if (!configured) {
-    HPC_CUDA_CHECK(cudaFuncSetAttribute(rgemm::gemm_bf16xfp32_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  const int smem = kSmemBytes;
+  if (int rc = configure_kernel()) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((m + rgemm::kBM - 1) / rgemm::kBM, n / tile_n, split_k);
   cfg.blockDim = dim3(rgemm::kThreads, 1, 1);

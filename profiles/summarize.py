@@ -17,6 +17,11 @@ KEYS = [
     "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
     "sm__cycles_elapsed.max", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "launch__cluster_size", "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
 ]
 
 
