@@ -541,11 +541,12 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
                        const Params& p, int grid, cudaStream_t stream) {
   using L = Smem<NQ>;
   auto kern = decode_attn_fp8_kernel<NQ, RL>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  const int dev = device_slot();
+  if (!configured[dev]) {
     HPC_CUDA_CHECK(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
+    configured[dev] = true;
   }
   kern<<<grid, kThreads, L::kTotal, stream>>>(tq, tk, tv, p);
   HPC_CUDA_CHECK(cudaGetLastError());

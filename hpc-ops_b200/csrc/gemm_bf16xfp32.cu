@@ -247,11 +247,12 @@ using namespace b200;  // NOLINT
 static constexpr int kSmemBytes = rgemm::kStageRegion + 256;
 
 static int configure_kernel() {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  const int dev = device_slot();
+  if (!configured[dev]) {
     HPC_CUDA_CHECK(cudaFuncSetAttribute(rgemm::gemm_bf16xfp32_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
+    configured[dev] = true;
   }
   return HPC_OK;
 }

@@ -487,18 +487,15 @@ constexpr int kSmemBytes = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGro
 template <bool kBlockwise, bool kFused>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
   auto kern = group_gemm_fp8_kernel<kBlockwise, kFused>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  const int dev = device_slot();
+  if (!configured[dev]) {
     HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
+    configured[dev] = true;
   }
-  // tile counters: a small rotating pool so back-to-back launches never share one
-  static int* counters = nullptr;
-  static unsigned launch_no = 0;
-  if (counters == nullptr) HPC_CUDA_CHECK(cudaMalloc(&counters, 64 * sizeof(int)));
   Params pp = p;
-  pp.tile_counter = counters + (launch_no++ % 64);
-  HPC_CUDA_CHECK(cudaMemsetAsync(pp.tile_counter, 0, sizeof(int), stream));
+  pp.tile_counter = launch_counter(stream);  // dynamic tile scheduler
+  if (pp.tile_counter == nullptr) return HPC_ERR_CUDA;
   kern<<<sm_count(), kThreads, kSmemBytes, stream>>>(ta, tb, pp);
   HPC_CUDA_CHECK(cudaGetLastError());
   return HPC_OK;

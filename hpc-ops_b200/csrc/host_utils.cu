@@ -27,6 +27,37 @@ int sm_count() {
   return cached[dev];
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < 64 ? dev : 63;
+}
+
+int* launch_counter(cudaStream_t stream) {
+  constexpr int kPool = 256;
+  static int* pool[64] = {nullptr};
+  static unsigned next[64] = {0};
+  static std::mutex mu;
+  const int dev = device_slot();
+  int* slot = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (pool[dev] == nullptr) {
+      if (cudaMalloc(&pool[dev], kPool * sizeof(int)) != cudaSuccess) {
+        set_last_error("launch_counter: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        pool[dev] = nullptr;
+        return nullptr;
+      }
+    }
+    slot = pool[dev] + (next[dev]++ % kPool);
+  }
+  if (cudaMemsetAsync(slot, 0, sizeof(int), stream) != cudaSuccess) {
+    set_last_error("launch_counter: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return slot;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

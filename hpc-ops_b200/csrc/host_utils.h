@@ -33,6 +33,13 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();
+// Current CUDA device clamped to [0, 63] (0 when the runtime is unavailable). Launchers keep their
+// one-time state (function attributes, scratch pools) per device: one process may drive several GPUs.
+int device_slot();
+// A zeroed int32 in device memory for one launch (dynamic tile / work counters): taken from a
+// rotating per-device pool of 256 and cleared with cudaMemsetAsync on `stream`. The pool is
+// allocated on the first call per device, which therefore must not happen inside a stream capture.
+int* launch_counter(cudaStream_t stream);
 
 // Encode a tiled TMA descriptor (uint8 elements). dims/strides innermost-first; strides in bytes for
 // dims 1..rank-1. Returns 0 on success.

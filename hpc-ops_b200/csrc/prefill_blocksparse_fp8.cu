@@ -637,11 +637,8 @@ static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, cons
   rc = encode_cache_map(&tv, vcache_ptr, num_head_kv, num_kvcache_blocks, v_blk, v_tok, v_head, &vhf);
   if (rc) return rc;
 
-  static int* counters = nullptr;
-  static unsigned launch_no = 0;
-  if (counters == nullptr) HPC_CUDA_CHECK(cudaMalloc(&counters, 64 * sizeof(int)));
-  int* counter = counters + (launch_no++ % 64);
-  HPC_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+  int* counter = launch_counter(stream);  // work-item counter of this launch
+  if (counter == nullptr) return HPC_ERR_CUDA;
 
   prefill::Params p;
   p.cu_seqlens_q = cu_seqlens_q_ptr;
