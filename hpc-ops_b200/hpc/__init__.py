@@ -46,3 +46,11 @@ _export_functions(_discover_modules())
 
 __version__ = _ffi.lib.hpc_version().decode()
 __built_json__ = _ffi.lib.hpc_built_json().decode()
+
+# torch.ops.hpc.version() / built_json(), as registered by reference src/C/version.cc:14
+from . import _ops as _ops_mod  # noqa: E402
+
+_ops_mod.define("version() -> str")
+_ops_mod.impl("version", lambda: __version__, "CompositeExplicitAutograd")
+_ops_mod.define("built_json() -> str")
+_ops_mod.impl("built_json", lambda: __built_json__, "CompositeExplicitAutograd")

@@ -49,6 +49,14 @@ lib.hpc_group_gemm_blockwise_fp8_async.restype = c_int
 lib.hpc_group_gemm_blockwise_fp8_async.argtypes = [c_ptr] * 11 + [c_int] * 10 + [c_ptr]
 lib.hpc_group_gemm_fp8_async.restype = c_int
 lib.hpc_group_gemm_fp8_async.argtypes = [c_ptr] * 10 + [c_int] * 8 + [c_ptr]
+lib.hpc_group_gemm_fp8_multistage_async.restype = c_int
+lib.hpc_group_gemm_fp8_multistage_async.argtypes = [c_ptr] * 9 + [c_int] * 7 + [c_ptr]
+lib.hpc_group_gemm_fp8_scatter_async.restype = c_int
+lib.hpc_group_gemm_fp8_scatter_async.argtypes = [c_ptr] * 10 + [c_int] * 7 + [c_ptr, c_int, c_ptr]
+lib.hpc_act_mul_and_quant_async.restype = c_int
+lib.hpc_act_mul_and_quant_async.argtypes = [c_ptr] * 3 + [c_int] * 3 + [c_ptr]
+lib.hpc_scaled_fp8_quant_async.restype = c_int
+lib.hpc_scaled_fp8_quant_async.argtypes = [c_ptr] * 3 + [c_i64, c_int, c_ptr]
 lib.hpc_reformat_x_scale_async.restype = c_int
 lib.hpc_reformat_x_scale_async.argtypes = [c_ptr] * 4 + [c_int] * 4 + [c_ptr]
 lib.hpc_count_and_gather_async.restype = c_int

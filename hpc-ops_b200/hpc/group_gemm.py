@@ -53,6 +53,52 @@ def _group_gemm_fp8_impl(x, weight, seqlens, cu_seqlens, y_scale, num_seq_per_gr
     return y
 
 
+def _cp_async_common(x, weight, y_scale, seqlens):
+    # reference src/group_gemm/cp_async/entry.cc:46-52
+    _require(x.is_cuda and weight.is_cuda, "inputs must be CUDA tensors")
+    _require(x.is_contiguous() and weight.is_contiguous(), "inputs must be contiguous")
+    _require(x.dtype == torch.float8_e4m3fn, "x must be float8_e4m3fn")
+    _require(weight.dtype == torch.float8_e4m3fn, "weight must be float8_e4m3fn")
+    _require(y_scale.dtype == torch.float32, "y_scale must be float32")
+    _require(seqlens.size(0) <= 512, "num_group must be <= 512")
+    _require(x.size(1) == weight.size(2), "x and weight must share the same k")
+
+
+def _group_gemm_fp8_cp_async_impl(x, weight, y_scale, seqlens, cu_seqlens, tiles, cu_tiles,
+                                  use_task_map=False):
+    # reference src/group_gemm/cp_async/entry.cc:41-92; tiles / cu_tiles / use_task_map are the
+    # reference's host-side schedule, not needed by the device-scheduled sm_100a kernel
+    _cp_async_common(x, weight, y_scale, seqlens)
+    m, k = x.shape
+    n = weight.size(1)
+    g = seqlens.size(0)
+    y = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    _check_rc(_lib.hpc_group_gemm_fp8_multistage_async(
+        _ptr(y), _ptr(x), _ptr(weight), _ptr(y_scale), _ptr(seqlens), _ptr(cu_seqlens), _ptr(tiles),
+        _ptr(cu_tiles), None, 0, m, n, k, g, (m // g) if g else 0, 0, _stream_of(x)),
+        "group_gemm_fp8_cp_async")
+    return y
+
+
+def _group_gemm_fp8_scatter_cp_async_impl(x, weight, y_scale, row_indices, seqlens, cu_seqlens,
+                                          tiles, cu_tiles, use_task_map=False):
+    # reference src/group_gemm/cp_async/entry.cc:94-142: x is a row pool, row i of the problem is
+    # x[row_indices[i]]; output rows are in compact order
+    _cp_async_common(x, weight, y_scale, seqlens)
+    _require(row_indices.dtype == torch.int32, "row_indices must be int32")
+    pool_rows, k = x.shape
+    m = row_indices.numel()
+    n = weight.size(1)
+    g = seqlens.size(0)
+    y = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    scratch = torch.empty((m, k), dtype=torch.float8_e4m3fn, device=x.device)
+    _check_rc(_lib.hpc_group_gemm_fp8_scatter_async(
+        _ptr(y), _ptr(x), _ptr(weight), _ptr(y_scale), _ptr(row_indices), _ptr(seqlens),
+        _ptr(cu_seqlens), _ptr(tiles), _ptr(cu_tiles), None, 0, m, n, k, g, (m // g) if g else 0, 0,
+        _ptr(scratch), pool_rows, _stream_of(x)), "group_gemm_fp8_scatter_cp_async")
+    return y
+
+
 def _group_gemm_blockwise_fp8_impl(x, weight, seqlens, cu_seqlens, xscale, wscale,
                                    num_seq_per_group_avg, output, tma_desc, task_map_workspace):
     # reference src/group_gemm/entry.cc:107-178
@@ -164,3 +210,26 @@ def _group_gemm_pertensor_fp8_fake(x, weight, seqlens, cu_seqlens, y_scale, num_
 def _group_gemm_blockwise_fp8_fake(x, weight, seqlens, cu_seqlens, xscale, wscale,
                                    num_seq_per_group_avg, output, tma_desc, task_map_workspace):
     return torch.empty((x.shape[0], weight.shape[1]), dtype=torch.bfloat16, device=x.device)
+
+_ops.define(
+    "group_gemm_fp8_cp_async(Tensor x, Tensor weight, Tensor y_scale, Tensor seqlens, Tensor "
+    "cu_seqlens, Tensor tiles, Tensor cu_tiles, bool use_task_map=False) -> (Tensor)")
+_ops.impl("group_gemm_fp8_cp_async", _group_gemm_fp8_cp_async_impl, "CUDA")
+_ops.define(
+    "group_gemm_fp8_scatter_cp_async(Tensor x, Tensor weight, Tensor y_scale, Tensor "
+    "row_indices, Tensor seqlens, Tensor cu_seqlens, Tensor tiles, Tensor cu_tiles, "
+    "bool use_task_map=False) -> (Tensor)")
+_ops.impl("group_gemm_fp8_scatter_cp_async", _group_gemm_fp8_scatter_cp_async_impl, "CUDA")
+
+
+@torch.library.register_fake("hpc::group_gemm_fp8_cp_async")
+def _group_gemm_fp8_cp_async_fake(x, weight, y_scale, seqlens, cu_seqlens, tiles, cu_tiles,
+                                  use_task_map=False):
+    return torch.empty((x.shape[0], weight.shape[1]), dtype=torch.bfloat16, device=x.device)
+
+
+@torch.library.register_fake("hpc::group_gemm_fp8_scatter_cp_async")
+def _group_gemm_fp8_scatter_cp_async_fake(x, weight, y_scale, row_indices, seqlens, cu_seqlens,
+                                          tiles, cu_tiles, use_task_map=False):
+    return torch.empty((row_indices.shape[0], weight.shape[1]), dtype=torch.bfloat16,
+                       device=x.device)

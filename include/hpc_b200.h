@@ -132,6 +132,33 @@ int hpc_reformat_x_scale_async(void* output_ptr, const void* xscale_ptr, const v
                                const void* cu_seqlens_ptr, int num_group, int m, int n, int tilem,
                                cudaStream_t stream);
 
+/* replaces reference src/group_gemm/cp_async/group_gemm.h:11-24 (the small-M cp.async grouped GEMMs:
+ * y[rows of g] = (x[rows of g] . w[g]^T) * y_scale[g], bf16 out). Served by the same tcgen05 grouped
+ * GEMM; tiles / cu_tiles / task_map are accepted and ignored. The scatter variant reads row i of
+ * the compact problem from row row_indices[i] of the pool x [pool_rows, k]; it needs an e4m3
+ * scratch of m * k bytes (gather_ptr) because the gather runs as a streaming pre-pass. */
+int hpc_group_gemm_fp8_multistage_async(
+    void* y_ptr, const void* x_ptr, const void* w_ptr, const void* y_scale_ptr,
+    const void* seqlens_ptr, const void* cu_seqlens_ptr, const void* tiles_ptr,
+    const void* cu_tiles_ptr, const void* task_map_ptr, int task_map_len, int m, int n, int k,
+    int num_group, int num_seq_per_group_avg, int use_pdl, cudaStream_t stream);
+int hpc_group_gemm_fp8_scatter_async(
+    void* y_ptr, const void* x_ptr, const void* w_ptr, const void* y_scale_ptr,
+    const void* row_indices_ptr, const void* seqlens_ptr, const void* cu_seqlens_ptr,
+    const void* tiles_ptr, const void* cu_tiles_ptr, const void* task_map_ptr, int task_map_len,
+    int m, int n, int k, int num_group, int num_seq_per_group_avg, int use_pdl, void* gather_ptr,
+    int pool_rows, cudaStream_t stream);
+
+/* ---- stand-alone activation / quantisation (HBM-bound streaming kernels) --------------------------
+ * replace reference src/activation/activation.h:15-17 (act_mul_and_quant_async: gate_up bf16
+ * [num_row, num_col = 2C] -> e4m3 [num_row, C] = silu(gate) * up * scale[0], optional bf16-rounded
+ * multiply) and :46-53 (scaled_fp8_quant_async: out = e4m3(in / scale[0]); in_dtype 0 = f32,
+ * 1 = f16, 2 = bf16). */
+int hpc_act_mul_and_quant_async(void* y_ptr, const void* x_ptr, const float* scale_ptr, int num_row,
+                                int num_col, int use_bf16_mul, cudaStream_t stream);
+int hpc_scaled_fp8_quant_async(void* y_ptr, const void* x_ptr, const float* scale_ptr,
+                               int64_t numel, int in_dtype, cudaStream_t stream);
+
 /* ---- FusedMoE -----------------------------------------------------------------------------------
  * replace reference src/fuse_moe/fuse_moe.h:15-62, argument for argument (bool -> int).
  * `intermediate_size` is gate_up_weight.size(1) (= 2*I) as in the reference entries.

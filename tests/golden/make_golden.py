@@ -201,7 +201,20 @@ def prefill_case(tag, k_per_token, seq, Hq, Hkv, skip, layout, seed):
     print("wrote prefill", tag, gt.shape)
 
 
+def act_case(tag, rows, half_cols, seed):
+    """tests/test_act.py:20-28 `_act_mul_and_quant`, executed unmodified on CPU."""
+    fn = extract(REF / "tests/test_act.py", "_act_mul_and_quant")
+    sys.path.insert(0, str(REPO))
+    from oracle import act as oact
+    gate_up, scale = oact.make_act_inputs(rows, half_cols, seed)
+    gt = fn(gate_up, scale)
+    np.savez_compressed(OUT / f"act_{tag}.npz", gate_up=gate_up.float().numpy(),
+                        scale=scale.numpy(), gt=u8(gt))
+    print("wrote act", tag, gt.shape)
+
+
 if __name__ == "__main__":
+    act_case("a", 64, 256, 41)
     prefill_case("kvpt", False, 384, 4, 1, 0.5, "nhd", 10086)
     prefill_case("kpertoken", True, 320, 4, 2, 0.5, "hnd", 10086)
     moe_blockwise_case("a", 24, 4, 256, 128, 8, 2, 1, True, 41)
