@@ -363,6 +363,7 @@ def main():
             "clocks": clocks,
         }))
     if dist is not None:
+        dist.barrier()  # ranks > 0 wait for rank 0's CPU baseline instead of tearing NCCL down early
         dist.destroy_process_group()
 
 
