@@ -101,7 +101,18 @@ struct Sched {
   int nt_count;
 };
 
-__device__ __forceinline__ bool decode_tile(const Sched& s, int tile, TileInfo& t) {
+// dynamic shared memory: operand stages, schedule arrays, amax exchange, barriers, tile queue, TMEM
+// slot; the cluster variant appends kTileQ more barriers behind that
+constexpr int kSmemBytesBase = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGroups) * 4 + 256 * 4 +
+                               (2 * kStages + 4 + 2 * kTileQ) * 8 + kTileQ * 4 + 16;
+constexpr int kSmemBytes = kSmemBytesBase + kTileQ * 8;
+static_assert(kSmemBytesBase % 8 == 0, "cluster barriers must be 8-byte aligned");
+
+// kPair: tiles are enumerated in units of two m-tiles (2u, 2u+1) of one (group, n-tile); CTA
+// `rank` of the 2-CTA cluster takes m-tile 2u + rank, which may lie past the group's last m-tile
+// (nvalid == 0: the CTA only relays its half of the weight tile).
+template <bool kPair>
+__device__ __forceinline__ bool decode_tile(const Sched& s, int tile, int rank, TileInfo& t) {
   if (tile >= s.cu_tiles[s.num_group]) return false;
   int lo = 0, hi = s.num_group - 1;
   while (lo < hi) {
@@ -116,16 +127,32 @@ __device__ __forceinline__ bool decode_tile(const Sched& s, int tile, TileInfo& 
   const int local = tile - s.cu_tiles[g];
   const int mtiles = (s.rows[g] + kBM - 1) / kBM;
   t.g = g;
-  t.nt = local / mtiles;
-  t.mt = local - t.nt * mtiles;
-  t.row0 = s.row_start[g] + t.mt * kBM;
-  const int left = s.rows[g] - t.mt * kBM;
-  t.nvalid = left < kBM ? left : kBM;
-  t.scol0 = s.pad_base[g] + t.mt * kBM;
+  if constexpr (kPair) {
+    const int munits = (mtiles + 1) >> 1;
+    t.nt = local / munits;
+    t.mt = 2 * (local - t.nt * munits) + rank;
+    t.row0 = s.row_start[g] + t.mt * kBM;
+    const int left = s.rows[g] - t.mt * kBM;
+    t.nvalid = left <= 0 ? 0 : (left < kBM ? left : kBM);
+    t.scol0 = s.pad_base[g] + t.mt * kBM;
+  } else {
+    t.nt = local / mtiles;
+    t.mt = local - t.nt * mtiles;
+    t.row0 = s.row_start[g] + t.mt * kBM;
+    const int left = s.rows[g] - t.mt * kBM;
+    t.nvalid = left < kBM ? left : kBM;
+    t.scol0 = s.pad_base[g] + t.mt * kBM;
+  }
   return true;
 }
 
-template <bool kBlockwise, bool kFused>
+// kCluster (experimental, HPC_B200_MOE_CLUSTER=1): the grid is launched as clusters of two CTAs that
+// work on the two m-tiles of one (group, n-tile) pair in lockstep. Each CTA fetches half of the
+// 256-row weight tile and TMA-multicasts it to both, so the L2 -> SM traffic per CTA and K block
+// drops from 48 KB to 32 KB (the measured bound of this kernel). Stage release (`empty`) needs both
+// CTAs' MMAs (multicast commit); CTA 0 claims the tiles and publishes them to CTA 1's queue through
+// distributed shared memory.
+template <bool kBlockwise, bool kFused, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
     group_gemm_fp8_kernel(const __grid_constant__ CUtensorMap tmap_a,
                           const __grid_constant__ CUtensorMap tmap_b, const Params p) {
@@ -145,6 +172,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tq_empty = tq_full + kTileQ;
   int* s_tileq = reinterpret_cast<int*>(tq_empty + kTileQ);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_tileq + kTileQ);
+  // cluster mode only: CTA 0's view of "CTA 1 has consumed queue slot i" (lives behind everything
+  // else so that the non-cluster layout is unchanged)
+  uint64_t* tq_peer = reinterpret_cast<uint64_t*>(smem + kSmemBytesBase);
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -161,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int r = g < p.num_group ? p.seqlens[g] : 0;
       const int mt = (r + kBM - 1) / kBM;
       const int pd = (r + p.scale_tile - 1) / p.scale_tile * p.scale_tile;
-      int it = mt * nt_count, ip = pd;
+      int it = (kCluster ? (mt + 1) / 2 : mt) * nt_count, ip = pd;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int a = __shfl_up_sync(0xffffffffu, it, o);
@@ -172,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       if (g < p.num_group) {
-        s_cu_tiles[g] = carry_tiles + it - mt * nt_count;
+        s_cu_tiles[g] = carry_tiles + it - (kCluster ? (mt + 1) / 2 : mt) * nt_count;
         s_pad_base[g] = carry_pad + ip - pd;
         s_rows[g] = r;
         s_row_start[g] = p.cu_seqlens[g];
@@ -187,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tensormap(&tmap_b);
     for (int i = 0; i < kStages; i++) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], kCluster ? 2 : 1);  // cluster: released by both CTAs' MMAs
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&part_full[i], 1);
@@ -196,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int i = 0; i < kTileQ; i++) {
       mbar_init(&tq_full[i], 1);
       mbar_init(&tq_empty[i], 9);  // MMA thread + 8 epilogue warps
+      if constexpr (kCluster) mbar_init(&tq_peer[i], 10);  // CTA 1: + its producer thread
     }
     fence_barrier_init();
   }
@@ -204,11 +236,34 @@ __global__ void __launch_bounds__(kThreads, 1)
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCluster) {
+    cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   Sched sched{s_cu_tiles, s_pad_base, s_rows, s_row_start, p.num_group, nt_count};
+  // consumer side of the tile queue: wait for slot `qs`, read it, release it
+  auto queue_wait = [&](uint32_t qs, uint32_t parity) {
+    if constexpr (kCluster) {
+      mbar_wait_cluster(&tq_full[qs], parity);
+    } else {
+      mbar_wait(&tq_full[qs], parity);
+    }
+  };
+  auto queue_release = [&](uint32_t qs) {
+    if constexpr (kCluster) {
+      if (crank == 0) {
+        mbar_arrive(&tq_empty[qs]);
+      } else {
+        mbar_arrive_cluster(map_to_cta(smem_u32(&tq_peer[qs]), 0));
+      }
+    } else {
+      mbar_arrive(&tq_empty[qs]);
+    }
+  };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -224,30 +279,57 @@ __global__ void __launch_bounds__(kThreads, 1)
       // Dynamic scheduler: tiles are claimed from a global counter, so tiles with neighbouring ids
       // (the m-tiles sharing one weight tile) start within a short window on different CTAs and
       // share that weight tile through L2. The id of the next tile is claimed one tile ahead.
-      int next_tile = atomicAdd(p.tile_counter, 1);
+      int next_tile = (!kCluster || crank == 0) ? atomicAdd(p.tile_counter, 1) : 0;
       while (true) {
-        const int tile = next_tile;
-        const bool valid = decode_tile(sched, tile, t);
-        {
+        int tile;
+        bool valid;
+        if (!kCluster || crank == 0) {
+          tile = next_tile;
+          valid = decode_tile<kCluster>(sched, tile, 0, t);
           const uint32_t qs = tq % kTileQ;
-          mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1);
+          const uint32_t par = ((tq / kTileQ) & 1) ^ 1;
+          mbar_wait(&tq_empty[qs], par);
           s_tileq[qs] = valid ? tile : -1;
+          if constexpr (kCluster) {
+            mbar_wait_cluster(&tq_peer[qs], par);  // CTA 1 is done with this slot as well
+            st_dsmem_u32(map_to_cta(smem_u32(&s_tileq[qs]), 1), static_cast<uint32_t>(valid ? tile : -1));
+            mbar_arrive_cluster(map_to_cta(smem_u32(&tq_full[qs]), 1));
+          }
           mbar_arrive(&tq_full[qs]);
           tq++;
+        } else {
+          const uint32_t qs = tq % kTileQ;
+          queue_wait(qs, (tq / kTileQ) & 1);
+          tile = s_tileq[qs];
+          queue_release(qs);
+          tq++;
+          valid = tile >= 0;
+          if (valid) decode_tile<kCluster>(sched, tile, 1, t);
         }
         if (!valid) break;
-        next_tile = atomicAdd(p.tile_counter, 1);
+        if (!kCluster || crank == 0) next_tile = atomicAdd(p.tile_counter, 1);
         const int nrow0 = kFused ? t.nt * 128 : t.nt * kBN;
         const int nrow1 = kFused ? p.n / 2 + t.nt * 128 : t.nt * kBN + 128;
         for (int kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
-          tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
-          tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+          if constexpr (kCluster) {
+            // the stage is free once BOTH CTAs have consumed it: this CTA writes into both
+            mbar_wait_cluster(&empty[s], ((it / kStages) & 1) ^ 1);
+            const bool real = t.nvalid > 0;
+            mbar_arrive_expect_tx(&full[s], real ? kStageBytes : kBBytes);
+            if (real) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+            // this CTA's half of the weight tile goes to both CTAs (same offsets, both `full`s)
+            tma_load_3d_mcast(b_dst + crank * (kBBytes / 2), &tmap_b, &full[s], kb * kBK,
+                              crank == 0 ? nrow0 : nrow1, t.g, static_cast<uint16_t>(3));
+          } else {
+            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[s], kStageBytes);
+            tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+            tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
+            tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+          }
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -261,12 +343,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       TileInfo t;
       while (true) {
         const uint32_t qs = tq % kTileQ;
-        mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
+        queue_wait(qs, (tq / kTileQ) & 1);
         const int tile = s_tileq[qs];
-        mbar_arrive(&tq_empty[qs]);
+        queue_release(qs);
         tq++;
         if (tile < 0) break;
-        decode_tile(sched, tile, t);
+        decode_tile<kCluster>(sched, tile, static_cast<int>(crank), t);
+        if constexpr (kCluster) {
+          if (t.nvalid == 0) {
+            // relay-only CTA of a pair: nothing to multiply, but both CTAs' stages must keep turning
+            for (int kb = 0; kb < KB; kb++, it++) {
+              const uint32_t s = it % kStages;
+              mbar_wait(&full[s], (it / kStages) & 1);  // the multicast data has landed here too
+              mbar_arrive(&empty[s]);
+              mbar_arrive_cluster(map_to_cta(smem_u32(&empty[s]), crank ^ 1u));
+            }
+            continue;
+          }
+        }
         for (int kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % kStages;
           const bool new_acc = kBlockwise || kb == 0;
@@ -281,7 +375,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int k = 0; k < 4; k++) {
             umma_f8(d, ad + k * 2, bd + k * 2, idesc, (k > 0) || !new_acc);
           }
-          umma_commit(&empty[s]);
+          if constexpr (kCluster) {
+            umma_commit_mcast(&empty[s], static_cast<uint16_t>(3));  // frees the stage in both CTAs
+          } else {
+            umma_commit(&empty[s]);
+          }
           if (kBlockwise || kb == KB - 1) {
             umma_commit(&part_full[buf]);
             acc_it++;
@@ -303,13 +401,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     TileInfo t;
     while (true) {
       const uint32_t qs = tq % kTileQ;
-      mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
+      queue_wait(qs, (tq / kTileQ) & 1);
       const int tile = s_tileq[qs];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tq_empty[qs]);
+      if (lane == 0) queue_release(qs);
       tq++;
       if (tile < 0) break;
-      decode_tile(sched, tile, t);
+      decode_tile<kCluster>(sched, tile, static_cast<int>(crank), t);
+      if constexpr (kCluster) {
+        if (t.nvalid == 0) continue;  // relay-only CTA: the MMA thread produces no accumulator
+      }
       const bool row_valid = row_local < t.nvalid;
       const int nb0 = kFused ? t.nt : t.nt * 2;
       const int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
@@ -477,16 +578,28 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCluster) {
+    cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it is done too
+  } else {
+    __syncthreads();
+  }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr int kSmemBytes = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGroups) * 4 + 256 * 4 +
-                           (2 * kStages + 4 + 2 * kTileQ) * 8 + kTileQ * 4 + 16;
+// HPC_B200_MOE_CLUSTER=1 selects the experimental 2-CTA weight-multicast variant (off by default:
+// not yet validated on hardware).
+static bool use_cluster_variant() {
+  static const bool on = [] {
+    const char* e = std::getenv("HPC_B200_MOE_CLUSTER");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
 
-template <bool kBlockwise, bool kFused>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
-  auto kern = group_gemm_fp8_kernel<kBlockwise, kFused>;
+template <bool kBlockwise, bool kFused, bool kCluster>
+static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
+                       cudaStream_t stream) {
+  auto kern = group_gemm_fp8_kernel<kBlockwise, kFused, kCluster>;
   static bool configured[64] = {false};
   const int dev = device_slot();
   if (!configured[dev]) {
@@ -496,9 +609,31 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   Params pp = p;
   pp.tile_counter = launch_counter(stream);  // dynamic tile scheduler
   if (pp.tile_counter == nullptr) return HPC_ERR_CUDA;
-  kern<<<sm_count(), kThreads, kSmemBytes, stream>>>(ta, tb, pp);
-  HPC_CUDA_CHECK(cudaGetLastError());
+  if constexpr (kCluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((sm_count() / 2) * 2, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, pp));
+  } else {
+    kern<<<sm_count(), kThreads, kSmemBytes, stream>>>(ta, tb, pp);
+    HPC_CUDA_CHECK(cudaGetLastError());
+  }
   return HPC_OK;
+}
+
+template <bool kBlockwise, bool kFused>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+  if (use_cluster_variant()) return launch_impl<kBlockwise, kFused, true>(ta, tb, p, stream);
+  return launch_impl<kBlockwise, kFused, false>(ta, tb, p, stream);
 }
 
 // Common launcher. mode bits: 1 = blockwise scales, 2 = fused activation epilogue.
