@@ -315,8 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
           if constexpr (kCluster) {
-            // the stage is free once BOTH CTAs have consumed it: this CTA writes into both
-            mbar_wait_cluster(&empty[s], ((it / kStages) & 1) ^ 1);
+            // the stage is free once BOTH CTAs have consumed it: this CTA writes into both. (A plain
+            // wait: nothing written by the consumers is read here; a cluster-scope acquire would
+            // invalidate L1 every K block.)
+            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
             const bool real = t.nvalid > 0;
             mbar_arrive_expect_tx(&full[s], real ? kStageBytes : kBBytes);
             if (real) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint32_t s = it % kStages;
               mbar_wait(&full[s], (it / kStages) & 1);  // the multicast data has landed here too
               mbar_arrive(&empty[s]);
-              mbar_arrive_cluster(map_to_cta(smem_u32(&empty[s]), crank ^ 1u));
+              mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&empty[s]), crank ^ 1u));
             }
             continue;
           }
