@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import hpc  # noqa: E402
 from hpc import _ffi  # noqa: E402
 from hpc import attention as hatt  # noqa: E402
-from oracle import attention as oa  # noqa: E402
+from synth import decode as oa  # noqa: E402
 
 
 def time_partial(d, B, Sq, Hkv, S, mpl, iters):

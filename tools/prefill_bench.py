@@ -14,7 +14,7 @@ sys.path.insert(0, str(REPO / "hpc-ops_b200"))
 import torch  # noqa: E402
 
 import hpc  # noqa: E402
-from oracle import prefill as op  # noqa: E402
+from synth import prefill as op  # noqa: E402
 
 
 def main():
