@@ -1,29 +1,13 @@
-// FP8 block-sparse (and dense) causal prefill attention over a paged KV cache (B200 / sm_100a).
-//
-// Replaces reference src/attention/prefill/kernels.cuh:1978-2554 (q per-token/head, k/v per-tensor)
-// and :2558-3150 (q per-token/head, k per-token/head in-cache scales, v per-head), their launcher
-// src/attention/prefill/warp_spec_with_kvcache_blocksparse_fp8_dim128.cu:19-253 and the varlen TMA
-// patch kernel (kernels.cuh:169-215, not needed here: Q is addressed with a 3-D descriptor).
-//
-// Work item = (batch, q head, 128-row Q tile); it visits only the 128x128 KV tiles that are set in
-// block_mask (absolute KV tile index, Q tile index relative to the request's first new token):
-//   active = { j < min(num_tile_kv, Kb) : mask[b, hq, mq, j] } U { Kb if Kb < num_tile_kv }
-// Items are handed out heaviest-first (largest mq first) by a global atomic counter.
-//
-// CTA = 256 threads, two CTAs resident per SM:
-//   warp 0     : TMA producer (Q tile, K pages -> 2-slot ring, V pages -> 2-slot ring, per-token k
-//                scales), builds the active-tile list of each item with ballot compaction
-//   warp 1     : tcgen05 issuer (one thread). S[128 q, 128 keys] = Q . K^T (K-major A/B);
-//                O[128 q, 128 d] += P . V with P K-major from smem and V MN-major exactly as it
-//                lies in the cache (no software transpose, unlike wgmma fp8: utils.cuh:461-521).
-//                QK(n+1) is issued as soon as the softmax threads hold S(n) in registers, i.e. it
-//                runs under softmax(n); PV(n) follows when P(n) is in smem.
-//   warps 4-7  : softmax, one thread per query row (row max / sum are thread-local): the whole S
-//                row (128 fp32) is pulled TMEM -> registers at once, then scale, causal/length
-//                mask, base-2 online softmax with a lazy reference maximum, P*256 -> e4m3 into
-//                128B-swizzled smem. O stays in TMEM across the tiles of an item (rare rescale by
-//                tcgen05.ld/st) and is read once by the epilogue.
-// TMEM: 256 columns per CTA (S at +0, O at +128).
+// Experimental variant of the FP8 block-sparse prefill kernel (prefill_blocksparse_fp8.cu) with TWO
+// softmax warpgroups per CTA (HPC_B200_PREFILL_WG2=1; off by default, NOT yet validated on
+// hardware). The one-warpgroup kernel is bound by the issue latency of its softmax: with two CTAs
+// per SM each scheduler hosts only two softmax warps (profiles/r1_prefill_v5_final.md: issue slots
+// 53 %, no pipe saturated). Here every query row is shared by two threads -- warps 4-7 own key
+// columns 0..63 of each tile, warps 8-11 columns 64..127 -- so four softmax warps per scheduler hide
+// each other's latency. Per tile the two threads of a row exchange their partial row maximum
+// through shared memory (one named barrier); row sums are combined once per item; each thread
+// rescales / writes its 64 of the 128 O columns. Producer and MMA roles, the mbarrier protocol and
+// the numerics are those of the one-warpgroup kernel (arrival counts 256 instead of 128).
 #include <cstdlib>
 #include <type_traits>
 
@@ -34,12 +18,12 @@
 namespace b200 {
 namespace prefill {
 
-constexpr int kThreads = 256;
+constexpr int kThreads2 = 384;
+constexpr int kXchBar = 2;  // named barrier of the 256 softmax threads
 
-// Two CTAs are resident per SM (each 256 threads, ~103 KB smem, 256 TMEM columns): the second CTA
-// fills the issue slots and the tensor pipe while the first one waits on a barrier.
+// Two CTAs are resident per SM (each 384 threads, ~106 KB smem, 256 TMEM columns).
 template <bool kKPerToken>
-struct Smem {
+struct Smem2 {
   static constexpr int kOffK = 0;                           // kStages x 16 KB
   static constexpr int kOffV = kOffK + kStages * kTileBytes;  // kStages x 16 KB
   static constexpr int kOffQ = kOffV + kStages * kTileBytes;  // 16 KB
@@ -50,27 +34,28 @@ struct Smem {
   static constexpr int kOffBar = kOffList + kListStride * 2;
   static constexpr int kNumBars = 4 * kStages + 5;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
-  static constexpr int kTotal = kOffTmem + 64;
+  // exchange between the two threads of a row: [2 tile-parity slots + 1 row-sum slot][2 halves][128 rows]
+  static constexpr int kOffXch = kOffTmem + 64;
+  static constexpr int kTotal = kOffXch + 3 * 2 * 128 * 4;
 };
 
 // Protocol (all mbarriers; "phase" = use-count parity), n = running KV-tile counter of the CTA:
 //   q_full      producer: item published (list + work id in smem, Q tile landed)
-//   q_empty     MMA thread (commit after the item's last QK) + 128 softmax threads (item finished)
+//   q_empty     MMA thread (commit after the item's last QK) + 256 softmax threads (item finished)
 //   k_full/k_empty[slot]   K ring; the slot is released by the commit after QK(n)
 //   v_full/v_empty[slot]   V ring; released by the commit after PV(n). v_empty also tells the
 //                          softmax threads that PV(n) is complete (P buffer free, O consistent)
 //   s_full      commit after QK(n)                            -> softmax
-//   s_free      128 softmax threads hold S(n) in registers     -> MMA thread may issue QK(n+1)
-//   p_full      128 softmax threads wrote P(n) (and rescaled O) -> MMA thread issues PV(n)
+//   s_free      256 softmax threads hold S(n) in registers     -> MMA thread may issue QK(n+1)
+//   p_full      256 softmax threads wrote P(n) (and rescaled O) -> MMA thread issues PV(n)
 // The k-scale buffer of tile n+2 was last read by softmax(n-2), which every softmax thread
 // finished before arriving on s_free(n-1), which precedes QK(n) and so the release of K slot n%2.
-// kPoly: exponentials per group of 8 scores that take the polynomial path (0, 2 or 4)
-template <bool kKPerToken, int kPoly>
-__global__ void __launch_bounds__(kThreads, 2)
-    prefill_blocksparse_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
-                                   const __grid_constant__ CUtensorMap tmap_k,
-                                   const __grid_constant__ CUtensorMap tmap_v, const Params p) {
-  using L = Smem<kKPerToken>;
+template <bool kKPerToken>
+__global__ void __launch_bounds__(kThreads2, 2)
+    prefill_blocksparse_fp8_wg2_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                                       const __grid_constant__ CUtensorMap tmap_k,
+                                       const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+  using L = Smem2<kKPerToken>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* k_smem = smem + L::kOffK;
   uint8_t* v_smem = smem + L::kOffV;
@@ -107,10 +92,10 @@ __global__ void __launch_bounds__(kThreads, 2)
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1 + 128);
+    mbar_init(q_empty, 1 + 256);
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -123,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
       // =========================== producer ==============================================
       const uint64_t pol_kv = make_policy_evict_last();  // KV of a request is re-read by its q-heads
@@ -274,12 +259,16 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    // =========================== softmax / epilogue =======================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // =========================== softmax / epilogue (two warpgroups) =======================
+    // Warps 4-7 take key columns 0..63 of every tile, warps 8-11 columns 64..127; the two threads of
+    // a row exchange their partial row maximum (per tile) and row sum (per item) through smem.
+    const int half = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row of the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float ks_tensor = kKPerToken ? 1.f : p.kscale[0];
+    float* xch = reinterpret_cast<float*>(smem + L::kOffXch);
 
     uint32_t n = 0;
     uint32_t item = 0;
@@ -295,35 +284,28 @@ __global__ void __launch_bounds__(kThreads, 2)
       const float qs = row_ok ? __ldg(p.qscale + (static_cast<long long>(k.b) * p.num_head_q + k.hq) *
                                                       p.qscale_ld + k.mq * kTile + row)
                               : 0.f;
-      // > 0 so that a masked score (-inf) stays -inf after scaling (an all-zero q row has qs = 0,
-      // and then every raw score is 0 as well)
       const float cq = fmaxf(qs * ks_tensor * p.softmax_scale_log2, 1e-30f);
-      // kv positions visible to this row: pos <= row_lim and pos < seq_kv
       const int row_lim = k.seq_kv - k.seq_q + k.mq * kTile + row;
       const int tile_lim_min = k.seq_kv - k.seq_q + k.mq * kTile;  // row 0
-      // Online softmax with a LAZY reference maximum `mref` (log2 units): P = 256 * 2^(s - mref).
-      // mref only moves when the tile maximum exceeds it by more than 0.75 (P would pass ~430 and
-      // approach the e4m3 limit 448) or when the row has not seen a key yet; only then are the
-      // row's O values in TMEM rescaled. With causal / block-sparse attention that happens on the
-      // first tiles of an item and rarely afterwards.
-      float mref = -INFINITY, lrun = 0.f;
+      // lazy reference maximum, as in the one-warpgroup kernel; both threads of a row take the same
+      // decisions because they see the same exchanged maximum
+      float mref = -INFINITY, lrun = 0.f;  // lrun: sum over THIS thread's columns only
       uint8_t* prow = p_smem + row * 128;
 
       auto softmax_tile = [&](auto mask_tag, const int i, const int key0, const float* ksr) {
         constexpr bool kMask = decltype(mask_tag)::value;
-        // ---- S row -> registers; S is then free for QK(n+1) ----
-        uint32_t sr[128];
-#pragma unroll
-        for (int c = 0; c < 4; c++) tmem_ld_x32(lane_addr + c * 32, sr + c * 32);
+        uint32_t sr[64];
+        tmem_ld_x32(lane_addr + half * 64, sr);
+        tmem_ld_x32(lane_addr + half * 64 + 32, sr + 32);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 8; c++) tmem_anchor16(sr + c * 16);
+        for (int c = 0; c < 4; c++) tmem_anchor16(sr + c * 16);
         tc_fence_before();
         mbar_arrive(s_free);
-        // ---- pass 1: dequantised (and masked) scores in place, row maximum ----
+        // ---- pass 1 over this thread's 64 columns ----
         float vmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int e0 = 0; e0 < 128; e0 += 8) {
+        for (int e0 = 0; e0 < 64; e0 += 8) {
           float v[8];
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
@@ -331,11 +313,11 @@ __global__ void __launch_bounds__(kThreads, 2)
             v[t] = __uint_as_float(sr[e]);
             v[t + 1] = __uint_as_float(sr[e + 1]);
             if constexpr (kKPerToken) {
-              const float2 ks2 = *reinterpret_cast<const float2*>(ksr + e);
+              const float2 ks2 = *reinterpret_cast<const float2*>(ksr + half * 64 + e);
               unpack_f2(fmul2(pack_f2(v[t], v[t + 1]), pack_f2(ks2.x, ks2.y)), v[t], v[t + 1]);
             }
             if constexpr (kMask) {
-              const int pos = key0 + e;
+              const int pos = key0 + half * 64 + e;
               v[t] = (pos > row_lim || pos >= k.seq_kv) ? -INFINITY : v[t];
               v[t + 1] = (pos + 1 > row_lim || pos + 1 >= k.seq_kv) ? -INFINITY : v[t + 1];
             }
@@ -347,7 +329,12 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
           for (int t = 0; t < 4; t++) vmax[t] = fmaxf(vmax[t], fmaxf(v[t], v[t + 4]));
         }
-        float tmax = fmaxf(fmaxf(vmax[0], vmax[1]), fmaxf(vmax[2], vmax[3])) * cq;
+        float hmax = fmaxf(fmaxf(vmax[0], vmax[1]), fmaxf(vmax[2], vmax[3]));
+        // ---- row maximum = max of the two halves (double-buffered exchange, one barrier) ----
+        float* xb = xch + (n & 1) * 256;
+        xb[half * 128 + row] = hmax;
+        named_bar_sync(kXchBar, 256);
+        float tmax = fmaxf(hmax, xb[(half ^ 1) * 128 + row]) * cq;
         if (!row_ok) tmax = -INFINITY;
         const bool update = (mref == -INFINITY) || (tmax > mref + 0.75f);
         const float mnew = update ? fmaxf(mref, tmax) : mref;
@@ -362,24 +349,24 @@ __global__ void __launch_bounds__(kThreads, 2)
           if (any_scale) {
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < 4; c++) {  // this thread's 64 of the 128 O columns
               uint32_t o[16];
-              tmem_ld_x16(lane_addr + 128 + c * 16, o);
+              tmem_ld_x16(lane_addr + 128 + half * 64 + c * 16, o);
               tmem_wait_ld();
               tmem_anchor16(o);
 #pragma unroll
               for (int e = 0; e < 16; e++) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st_x16(lane_addr + 128 + c * 16, o);
+              tmem_st_x16(lane_addr + 128 + half * 64 + c * 16, o);
             }
             tmem_wait_st();
           }
         }
-        // ---- pass 2: P = 256 * 2^(s - mref) -> e4m3, row sum ----
+        // ---- pass 2: P = 256 * 2^(s - mref) -> e4m3 (this thread's four 16-byte chunks) ----
         const uint64_t bias2 = dead ? pack_f2(-INFINITY, -INFINITY) : pack_f2(8.f - mnew, 8.f - mnew);
         const uint64_t cq2 = pack_f2(cq, cq);
         uint64_t psum2[2] = {0ull, 0ull};
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
+        for (int c = 0; c < 4; c++) {
           uint32_t packed[4];
 #pragma unroll
           for (int q4 = 0; q4 < 4; q4++) {
@@ -387,23 +374,17 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
             for (int t = 0; t < 4; t += 2) {
               const int e = c * 16 + q4 * 4 + t;
-              const uint64_t x2 =
-                  ffma2(pack_f2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), cq2, bias2);
-              const bool poly = (t == 2) && (kPoly == 4 || (kPoly == 2 && (q4 & 1)));
-              if (poly) {
-                exp2_poly_pair(x2, e4[t], e4[t + 1]);
-              } else {
-                float x0, x1;
-                unpack_f2(x2, x0, x1);
-                e4[t] = exp2_approx(x0);
-                e4[t + 1] = exp2_approx(x1);
-              }
+              float x0, x1;
+              unpack_f2(ffma2(pack_f2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), cq2, bias2),
+                        x0, x1);
+              e4[t] = exp2_approx(x0);
+              e4[t + 1] = exp2_approx(x1);
               psum2[t >> 1] = fadd2(psum2[t >> 1], pack_f2(e4[t], e4[t + 1]));
             }
             packed[q4] = cvt_e4m3x4(e4[0], e4[1], e4[2], e4[3]);
           }
-          // 16 keys = 16-B chunk c of this row, 128B swizzle: chunk ^ (row & 7)
-          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) =
+          // 16 keys = 16-B chunk (half * 4 + c) of this row, 128B swizzle: chunk ^ (row & 7)
+          *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (row & 7)) << 4)) =
               make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
         float s0, s1, s2, s3;
@@ -430,22 +411,29 @@ __global__ void __launch_bounds__(kThreads, 2)
         n++;
       }
       mbar_arrive(q_empty);  // the list / work slot may be refilled by the producer
-      // ---- epilogue: O / sum * vscale -> bf16 row ----
+      // ---- row sum = sum of the two halves. Its own slot (the tile-parity slots may already be
+      // rewritten by a thread that has moved on to the next item); the first barrier makes sure
+      // every thread has read the previous item's sums before they are overwritten ----
+      float* lb = xch + 2 * 256;
+      named_bar_sync(kXchBar, 256);
+      lb[half * 128 + row] = lrun;
+      named_bar_sync(kXchBar, 256);
+      const float lsum = lrun + lb[(half ^ 1) * 128 + row];
+      // ---- epilogue: O / sum * vscale -> bf16, this thread's 64 of the 128 output columns ----
       if (nact > 0) {
         mbar_wait(&v_empty[(n - 1) % kStages], ((n - 1) / kStages) & 1);  // last PV of the item
         tc_fence_after();
       }
       {
-        const float vs = kKPerToken ? __ldg(p.vscale + hkv) : p.vscale[0];  // (v/256)/(sum/256)
-        // a row whose every visible tile was skipped has sum 0 -> NaN, as documented for the
-        // reference (hpc/attention.py:274-277)
-        const float inv = vs / lrun;
-        __nv_bfloat16* dst = p.out + static_cast<long long>(k.q0 + row) * p.ld_out + k.hq * kD;
+        const float vs = kKPerToken ? __ldg(p.vscale + hkv) : p.vscale[0];
+        const float inv = vs / lsum;  // all-skipped row: 0 / 0 -> NaN, as documented for the reference
+        __nv_bfloat16* dst =
+            p.out + static_cast<long long>(k.q0 + row) * p.ld_out + k.hq * kD + half * 64;
 #pragma unroll 1
-        for (int c = 0; c < 8; c++) {
+        for (int c = 0; c < 4; c++) {
           uint32_t o[16];
           if (nact > 0) {
-            tmem_ld_x16(lane_addr + 128 + c * 16, o);
+            tmem_ld_x16(lane_addr + 128 + half * 64 + c * 16, o);
             tmem_wait_ld();
             tmem_anchor16(o);
           } else {
@@ -487,164 +475,22 @@ __global__ void __launch_bounds__(kThreads, 2)
 
 using namespace b200;  // NOLINT
 
-constexpr int kDefaultPoly = 2;
-
-static int encode_cache_map(CUtensorMap* tm, const void* base, int heads, int num_blocks,
-                            int64_t blk_stride, int64_t tok_stride, int64_t head_stride,
-                            int* head_first) {
-  *head_first = head_stride <= tok_stride ? 1 : 0;
-  uint64_t dims[4];
-  uint64_t strides[3];
-  uint32_t box[4];
-  dims[0] = 128;
-  box[0] = 128;
-  if (*head_first) {
-    dims[1] = static_cast<uint64_t>(heads);
-    dims[2] = 64;
-    strides[0] = static_cast<uint64_t>(head_stride);
-    strides[1] = static_cast<uint64_t>(tok_stride);
-    box[1] = 1;
-    box[2] = 64;
-  } else {
-    dims[1] = 64;
-    dims[2] = static_cast<uint64_t>(heads);
-    strides[0] = static_cast<uint64_t>(tok_stride);
-    strides[1] = static_cast<uint64_t>(head_stride);
-    box[1] = 64;
-    box[2] = 1;
-  }
-  dims[3] = static_cast<uint64_t>(num_blocks);
-  strides[2] = static_cast<uint64_t>(blk_stride);
-  box[3] = 1;
-  const CUtensorMapL2promotion promo = (tok_stride == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                                           : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-  return encode_tmap_u8(tm, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, promo);
-}
-
-// Common launcher of the two quant schemes.
-static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, const void* kcache_ptr,
-                          const void* vcache_ptr, const float* qscale_ptr, const float* kscale_ptr,
-                          const float* vscale_ptr, const int* cu_seqlens_q_ptr,
-                          const int* block_ids_ptr, const int* seqlens_kv_ptr,
-                          const uint8_t* block_mask_ptr, int num_batch, int total_seq_q,
-                          int max_seq_q, int num_head_q, int num_head_kv, int num_dim,
-                          int num_kvcache_blocks, int block_size, int max_blocks, int qscale_ld,
-                          int mask_mq, int mask_kb, int ldY, int ldQ, int64_t k_blk, int64_t k_tok,
-                          int64_t k_head, int64_t v_blk, int64_t v_tok, int64_t v_head,
-                          int64_t ks_blk, int64_t ks_grp, int64_t ks_head, cudaStream_t stream) {
-  HPC_REQUIRE(num_dim == 128, "blocksparse prefill: head dim must be 128");
-  HPC_REQUIRE(block_size == 64, "blocksparse prefill: paged block size must be 64 in this build");
-  HPC_REQUIRE(num_head_kv > 0 && num_head_q % num_head_kv == 0, "bad head counts");
-  HPC_REQUIRE(num_batch > 0 && max_seq_q > 0, "bad batch / max_seqlens_q");
-  HPC_REQUIRE((ldQ % 16) == 0 && (reinterpret_cast<uintptr_t>(q_ptr) & 15) == 0, "q alignment");
-  if (total_seq_q <= 0) return HPC_OK;
-
-  CUtensorMap tq, tk, tv;
-  {
-    uint64_t dims[3] = {128, static_cast<uint64_t>(num_head_q), static_cast<uint64_t>(total_seq_q)};
-    uint64_t strides[2] = {128, static_cast<uint64_t>(ldQ)};
-    uint32_t box[3] = {128, 1, 128};
-    int rc = encode_tmap_u8(&tq, q_ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-    if (rc) return rc;
-  }
-  int khf = 1, vhf = 1;
-  int rc = encode_cache_map(&tk, kcache_ptr, num_head_kv, num_kvcache_blocks, k_blk, k_tok, k_head, &khf);
-  if (rc) return rc;
-  rc = encode_cache_map(&tv, vcache_ptr, num_head_kv, num_kvcache_blocks, v_blk, v_tok, v_head, &vhf);
-  if (rc) return rc;
-
-  int* counter = launch_counter(stream);  // work-item counter of this launch
-  if (counter == nullptr) return HPC_ERR_CUDA;
-
-  prefill::Params p;
-  p.cu_seqlens_q = cu_seqlens_q_ptr;
-  p.seqlens_kv = seqlens_kv_ptr;
-  p.block_ids = block_ids_ptr;
-  p.block_mask = block_mask_ptr;
-  p.qscale = qscale_ptr;
-  p.kscale = kscale_ptr;
-  p.vscale = vscale_ptr;
-  p.out = static_cast<__nv_bfloat16*>(y_ptr);
-  p.work_counter = counter;
-  p.ks_stride_blk = ks_blk;
-  p.ks_stride_grp = ks_grp;
-  p.ks_stride_head = ks_head;
-  p.num_batch = num_batch;
-  p.num_head_q = num_head_q;
-  p.num_head_kv = num_head_kv;
-  p.group = num_head_q / num_head_kv;
-  p.max_q_tiles = (max_seq_q + prefill::kTile - 1) / prefill::kTile;
-  p.mask_mq = mask_mq;
-  p.mask_kb = mask_kb;
-  p.max_blocks = max_blocks;
-  p.qscale_ld = qscale_ld;
-  p.ld_out = ldY;
-  p.k_head_first = khf;
-  p.v_head_first = vhf;
-  p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(128.f);
-
-  static const bool wg2 = [] {
-    const char* e = std::getenv("HPC_B200_PREFILL_WG2");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (wg2) return prefill_wg2_launch(k_per_token, tq, tk, tv, p, stream);  // experimental variant
-
-  const int grid = 2 * sm_count();  // two resident CTAs per SM
-  // share of exponentials on the FMA pipe: HPC_B200_PREFILL_POLY = 0 | 2 | 4 (per 8 scores)
-  static const int poly = [] {
-    const char* e = std::getenv("HPC_B200_PREFILL_POLY");
-    const int v = e ? std::atoi(e) : kDefaultPoly;
-    return (v == 0 || v == 2 || v == 4) ? v : kDefaultPoly;
-  }();
-  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, prefill::Params);
-  KernelFn kern;
-  int smem_bytes;
+// Launcher used by prefill_launch() when HPC_B200_PREFILL_WG2=1 (tensor maps and Params are built
+// there; `p.work_counter` is already set).
+int prefill_wg2_launch(bool k_per_token, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const prefill::Params& p, cudaStream_t stream) {
+  const int grid = 2 * sm_count();
   if (k_per_token) {
-    smem_bytes = prefill::Smem<true>::kTotal;
-    kern = poly == 4   ? prefill::prefill_blocksparse_fp8_kernel<true, 4>
-           : poly == 2 ? prefill::prefill_blocksparse_fp8_kernel<true, 2>
-                       : prefill::prefill_blocksparse_fp8_kernel<true, 0>;
+    auto kern = prefill::prefill_blocksparse_fp8_wg2_kernel<true>;
+    HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        prefill::Smem2<true>::kTotal));
+    kern<<<grid, prefill::kThreads2, prefill::Smem2<true>::kTotal, stream>>>(tq, tk, tv, p);
   } else {
-    smem_bytes = prefill::Smem<false>::kTotal;
-    kern = poly == 4   ? prefill::prefill_blocksparse_fp8_kernel<false, 4>
-           : poly == 2 ? prefill::prefill_blocksparse_fp8_kernel<false, 2>
-                       : prefill::prefill_blocksparse_fp8_kernel<false, 0>;
+    auto kern = prefill::prefill_blocksparse_fp8_wg2_kernel<false>;
+    HPC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        prefill::Smem2<false>::kTotal));
+    kern<<<grid, prefill::kThreads2, prefill::Smem2<false>::kTotal, stream>>>(tq, tk, tv, p);
   }
-  HPC_CUDA_CHECK(cudaFuncSetAttribute(reinterpret_cast<const void*>(kern),
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  kern<<<grid, prefill::kThreads, smem_bytes, stream>>>(tq, tk, tv, p);
   HPC_CUDA_CHECK(cudaGetLastError());
   return HPC_OK;
-}
-
-#define PREFILL_PARAMS                                                                             \
-  void *y_ptr, const void *q_ptr, const void *kcache_ptr, const void *vcache_ptr,                 \
-      const float *qscale_ptr, const float *kscale_ptr, const float *vscale_ptr,                  \
-      const int *cu_seqlens_q_ptr, const int *block_ids_ptr, const int *seqlens_kv_ptr,           \
-      const uint8_t *block_mask_ptr, int num_batch, int total_seq_q, int max_seq_q,               \
-      int num_head_q, int num_head_kv, int num_dim, int num_kvcache_blocks, int block_size,       \
-      int max_blocks, int qscale_ld, int mask_mq, int mask_kb, int ldY, int ldQ, int64_t k_blk,   \
-      int64_t k_tok, int64_t k_head, int64_t v_blk, int64_t v_tok, int64_t v_head
-#define PREFILL_ARGS                                                                               \
-  y_ptr, q_ptr, kcache_ptr, vcache_ptr, qscale_ptr, kscale_ptr, vscale_ptr, cu_seqlens_q_ptr,     \
-      block_ids_ptr, seqlens_kv_ptr, block_mask_ptr, num_batch, total_seq_q, max_seq_q,           \
-      num_head_q, num_head_kv, num_dim, num_kvcache_blocks, block_size, max_blocks, qscale_ld,    \
-      mask_mq, mask_kb, ldY, ldQ, k_blk, k_tok, k_head, v_blk, v_tok, v_head
-
-// replaces reference src/attention/prefill/prefill.h:46-54
-// (attention_with_kvcache_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async)
-extern "C" int hpc_attention_blocksparse_prefill_qpertoken_perhead_kvpertensor_fp8_async(
-    PREFILL_PARAMS, cudaStream_t stream) {
-  return prefill_launch(false, PREFILL_ARGS, 0, 0, 0, stream);
-}
-
-// replaces reference src/attention/prefill/prefill.h:55-63
-// (attention_with_kvcache_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async);
-// ks_* = strides in floats of the k-scale tensor [blocks, block/32, Hkv, 32]
-extern "C" int hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async(
-    PREFILL_PARAMS, int64_t ks_blk, int64_t ks_grp, int64_t ks_head, cudaStream_t stream) {
-  HPC_REQUIRE(ks_grp % 4 == 0 && ks_head % 4 == 0 && ks_blk % 4 == 0,
-              "k scale strides must be multiples of 4 floats (16-byte bulk copies)");
-  return prefill_launch(true, PREFILL_ARGS, ks_blk, ks_grp, ks_head, stream);
 }
