@@ -213,7 +213,46 @@ def act_case(tag, rows, half_cols, seed):
     print("wrote act", tag, gt.shape)
 
 
+def allreduce_case(tag, world, n, hidden, seed):
+    """tests/test_fuse_allreduce_rmsnorm_high_throughput.py:15-29 `ref_allreduce_rmsnorm` (+ `rmsnorm`),
+    executed unmodified on CPU."""
+    ns = extract_many(REF / "tests/test_fuse_allreduce_rmsnorm_high_throughput.py",
+                      {"rmsnorm", "ref_allreduce_rmsnorm"})
+    from oracle import allreduce as oar
+    xs, residual, weight, n_pad = oar.make_inputs(world, n, hidden, seed)
+    res, out = ns["ref_allreduce_rmsnorm"](xs, residual, weight, 1e-6)
+    np.savez_compressed(OUT / f"allreduce_{tag}.npz", meta=np.array([world, n, hidden, seed]),
+                        out_residual=res.float().numpy(), out=out.float().numpy())
+    print("wrote allreduce", tag, out.shape)
+
+
+def group_gemm_cases():
+    """tests/test_group_gemm_pertensor.py:20-44 and tests/test_group_gemm_blockwise.py:20-47, executed
+    unmodified on CPU (torch._scaled_mm has a CPU kernel in torch 2.11)."""
+    g = torch.Generator().manual_seed(7)
+    G, per, n, k = 4, 24, 256, 256
+    seqlens = torch.tensor([24, 0, 7, 16], dtype=torch.int32)
+    cu = torch.arange(G, dtype=torch.int32) * per  # groups start at multiples of `per` (padded m)
+    m = G * per
+    x = torch.randn((m, k), generator=g).to(torch.float8_e4m3fn)
+    w = torch.randn((G, n, k), generator=g).to(torch.float8_e4m3fn)
+    scale = torch.tensor(0.37, dtype=torch.float32)
+    fn = extract(REF / "tests/test_group_gemm_pertensor.py", "naive_group_gemm_pertensor_fp8")
+    y_pt = fn(x, w, seqlens, cu, scale)
+    xscale = torch.rand((k // 128, m), generator=g) + 0.5
+    wscale = torch.rand((G, n // 128, k // 128), generator=g) + 0.5
+    fn2 = extract(REF / "tests/test_group_gemm_blockwise.py", "naive_group_gemm")
+    y_bw = fn2(x, w, seqlens, cu, xscale, wscale)
+    np.savez_compressed(OUT / "group_gemm_a.npz", x=u8(x), w=u8(w), seqlens=seqlens.numpy(),
+                        cu=cu.numpy(), scale=scale.numpy(), xscale=xscale.numpy(),
+                        wscale=wscale.numpy(), y_pertensor=y_pt.float().numpy(),
+                        y_blockwise=y_bw.float().numpy(), per=np.array([per]))
+    print("wrote group_gemm a", y_pt.shape)
+
+
 if __name__ == "__main__":
+    allreduce_case("w4", 4, 13, 512, 10001)
+    group_gemm_cases()
     act_case("a", 64, 256, 41)
     prefill_case("kvpt", False, 384, 4, 1, 0.5, "nhd", 10086)
     prefill_case("kpertoken", True, 320, 4, 2, 0.5, "hnd", 10086)

@@ -48,3 +48,28 @@ def test_pertensor_oracle_matches_reference_function():
                               rank_ep)
     ref = torch.from_numpy(z["out"])
     assert torch.allclose(y.float(), ref, rtol=0.08, atol=0.1), (y.float() - ref).abs().max()
+
+
+def test_group_gemm_oracles_match_reference_functions():
+    """Stand-alone grouped GEMM oracles vs the reference's naive functions
+    (tests/test_group_gemm_pertensor.py:20-44, tests/test_group_gemm_blockwise.py:20-47)."""
+    z = np.load(G / "group_gemm_a.npz")
+    x, w = _f8(z["x"]), _f8(z["w"])
+    seqlens, cu = torch.from_numpy(z["seqlens"]), torch.from_numpy(z["cu"])
+    per = int(z["per"][0])
+    Gn = w.shape[0]
+    # per-tensor: the reference passes `scale` as scale_a and scale_b of _scaled_mm -> y * scale^2
+    s2 = float(z["scale"]) ** 2
+    cu_full = torch.cat([cu, torch.tensor([Gn * per], dtype=torch.int32)])
+    y = om.group_gemm_pertensor(x, w, cu_full, torch.full((Gn,), s2))
+    y_bw = om.group_gemm_blockwise_standalone(x, w, seqlens, cu, torch.from_numpy(z["xscale"]),
+                                              torch.from_numpy(z["wscale"]), per)
+    ref_pt, ref_bw = torch.from_numpy(z["y_pertensor"]), torch.from_numpy(z["y_blockwise"])
+    for g in range(Gn):
+        s, c = int(cu[g]), int(seqlens[g])
+        assert torch.allclose(y[s:s + c].float(), ref_pt[s:s + c], rtol=1e-2, atol=1e-2), g
+        # the reference function multiplies in bf16 on the CPU (blocked bf16 accumulation); the
+        # oracle accumulates the same bf16-rounded operands in fp32 -> compare at the tolerance the
+        # reference test itself uses (tests/test_group_gemm_blockwise.py:84)
+        assert torch.allclose(y_bw[s:s + c].float(), ref_bw[s:s + c], rtol=0.08, atol=0.1), g
+        assert (ref_pt[s + c:s + per] == 0).all() and (ref_bw[s + c:s + per] == 0).all()
