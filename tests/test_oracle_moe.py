@@ -68,8 +68,9 @@ def test_group_gemm_oracles_match_reference_functions():
     for g in range(Gn):
         s, c = int(cu[g]), int(seqlens[g])
         assert torch.allclose(y[s:s + c].float(), ref_pt[s:s + c], rtol=1e-2, atol=1e-2), g
-        # the reference function multiplies in bf16 on the CPU (blocked bf16 accumulation); the
-        # oracle accumulates the same bf16-rounded operands in fp32 -> compare at the tolerance the
-        # reference test itself uses (tests/test_group_gemm_blockwise.py:84)
-        assert torch.allclose(y_bw[s:s + c].float(), ref_bw[s:s + c], rtol=0.08, atol=0.1), g
+        # the reference function multiplies in bf16; executed on the CPU (as the fixture was) that
+        # GEMM accumulates in bf16 blocks, i.e. it is noisier than the oracle, which accumulates the
+        # same bf16-rounded operands in fp32. rtol is the reference test's (test_group_gemm_blockwise.py:84),
+        # atol covers the fixture's own accumulation noise (outputs reach |82|, bf16 ulp there = 0.5)
+        assert torch.allclose(y_bw[s:s + c].float(), ref_bw[s:s + c], rtol=0.08, atol=0.3), g
         assert (ref_pt[s + c:s + per] == 0).all() and (ref_bw[s + c:s + per] == 0).all()
