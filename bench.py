@@ -15,8 +15,14 @@ A step = one decode-attention pass over that batch: task-map assign + split-k at
   roofline   the attention kernel alone: algorithmic bytes / its CUDA-event duration vs measured HBM.
   cpu_baseline  the torch CPU oracle on a bounded sample of the same workload.
 
-N>1: the path does not shard (SURVEY.md §8e "replicas only"): every rank runs the same workload on
-its own GPU, no data-path collective; value = N * tokens / max-over-ranks time ("weak").
+  extra      the other BASELINE configs, each with its own roofline fraction and a sampled parity
+             check against the CPU oracle (tools/bench_extras.py): FusedMoE C3, block-sparse prefill
+             C4 (both quant schemes), the route GEMM, and the fused AllReduce+RMSNorm C5.
+
+N>1: decode does not shard (SURVEY.md §8e "replicas only"): every rank runs the same decode workload
+on its own GPU, no data-path collective; value = N * tokens / max-over-ranks time ("weak"). The ONE
+sharded path, fuse_allreduce_rmsnorm, runs at W=N inside `extra.allreduce_c5` (high-throughput and
+low-latency kernels over the NCCL-initialised symmetric buffers, CUDA-graph timed, max over ranks).
 `--impl reference`: times the reference's own algorithm on the host cores (the torch CPU reference
 path restated in oracle/, since the reference's sm_90a build cannot execute on sm_100).
 """
@@ -38,8 +44,20 @@ import torch  # noqa: E402
 WORKLOAD = dict(num_batch=64, num_seq_q=1, num_head_kv=8, num_head_q=32, head_dim=128, seq=8192,
                 block_size=64)
 WORKLOAD_NAME = "fp8_decode_attn bs=64 GQA32/8 d=128 seq=8192 page=64 (BASELINE configs[1])"
+LAUNCHES_PER_STEP = 3   # assign_task_kernel, decode_attn_fp8_kernel, decode_combine_kernel
+EXTRA_BUDGET_S = 420    # the `extra` block must not delay the line beyond this
 METRIC = "fp8_decode_attn_tokens_per_s"
 UNIT = "tok/s"
+
+
+MPL = 64  # reference benchmark default (benchmark/attention_decode/bench_attention_decode_fp8.py:710)
+
+
+def config_dict(world):
+    """`config` of the JSON line: identical in both arms."""
+    return {"workload": WORKLOAD_NAME, "parallelism": f"replicas x{world}",
+            "step": "task-map assign + split-k attention + combine", "min_process_len": MPL,
+            "l2": "inputs (1.07 GB KV per step) exceed the 126 MB L2; no flush needed"}
 
 
 def algorithmic_bytes(w):
@@ -122,10 +140,13 @@ def cpu_oracle_sample(w, d, nreq, gpu_out=None):
                ("block_ids", "kv_lens_total") else v).cpu() for k, v in d.items()}
     args = (sub["q"], sub["kvcache"][:, 0], sub["kvcache"][:, 1], sub["block_ids"],
             sub["kv_lens_total"], sub["q_scale"], sub["k_scale"], sub["v_scale"], w["num_seq_q"])
-    oa.decode_fp8_kvpertensor(*[a[:1] if i in (0, 3, 4, 5) else a for i, a in enumerate(args)])  # warm-up
-    t0 = time.perf_counter()
-    gt = oa.decode_fp8_kvpertensor(*args)
-    dt = time.perf_counter() - t0
+    oa.decode_fp8_kvpertensor(*args)  # warm-up (thread pool, page faults)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        gt = oa.decode_fp8_kvpertensor(*args)
+        times.append(time.perf_counter() - t0)
+    dt = sorted(times)[1]  # median of 3
     err = None
     if gpu_out is not None:
         err = (gpu_out[:nreq * w["num_seq_q"]].float().cpu() - gt.float()).abs().max().item()
@@ -157,9 +178,10 @@ def run_reference(a, rank, world):
     sample = f"{nreq} of 64 requests per step (requests are independent), torch CPU oracle"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3 * (64 / nreq),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp8_e4m3",
-        "data": "synthetic", "config": {"workload": WORKLOAD_NAME},
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+        "ms_per_full_batch_extrapolated": dt / a.steps * 1e3 * (64 / nreq),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp8_e4m3 (fp32 accumulate)", "data": "synthetic", "config": config_dict(world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(),
                          "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -173,6 +195,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (C3/C4/C5/route GEMM)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,7 +228,6 @@ def main():
     B, Sq, Hkv, Hq, S = w["num_batch"], w["num_seq_q"], w["num_head_kv"], w["num_head_q"], w["seq"]
     d = make_decode_fp8_inputs(B, Sq, [S] * B, Hkv, Hq, seed=41 + rank, device=dev)
     kc, vc = d["kvcache"][:, 0], d["kvcache"][:, 1]
-    MPL = 64  # reference benchmark default (benchmark/attention_decode/bench_attention_decode_fp8.py:710)
     task_map = hpc.get_attention_decode_task_workspace(B, S, Hkv, MPL)
     hpc.assign_attention_decode_task(d["kv_lens_total"], task_map, Hkv, Sq, True, MPL)
     out = torch.empty((B * Sq, Hq, 128), dtype=torch.bfloat16, device=dev)
@@ -229,20 +251,25 @@ def main():
         sampler.start()
 
     # ---------------- value: inputs resident in HBM ----------------
+    # Each timed region is EXACTLY K steps between barrier + synchronize; short runs (small K) are
+    # repeated until >= 200 steps have been timed and the median region is reported.
     for _ in range(a.warmup):
         step_resident()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        step_resident()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    repeats = max(1, -(-200 // a.steps))
+    region_ms = []
+    for _ in range(repeats):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step_resident()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_ms.append(float(t.item()))
+    ms_total = sorted(region_ms)[len(region_ms) // 2]
     ms_per_step = ms_total / a.steps
     value = world * B * Sq / (ms_per_step * 1e-3)
 
@@ -333,6 +360,7 @@ def main():
 
     clocks = sampler.stop() if rank == 0 else None
 
+    line = None
     if rank == 0:
         # CPU baseline on a bounded sample (torch oracle == the reference's CPU-runnable path)
         torch.set_num_threads(os.cpu_count() or 1)
@@ -340,34 +368,87 @@ def main():
         step_resident()
         torch.cuda.synchronize()
         cpu_val, cpu_dt, cpu_err = cpu_oracle_sample(w, d, nreq, out)
-        print(json.dumps({
+        line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp8_e4m3 (fp32 accumulate)",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "parallelism": f"replicas x{world}",
-                       "step": "task-map assign + split-k attention + combine",
-                       "min_process_len": MPL,
-                       "l2": "inputs (1.07 GB KV per step) exceed the 126 MB L2; no flush needed"},
+            "data": "synthetic", "config": config_dict(world),
+            "timed_regions": {"count": repeats, "steps_each": a.steps,
+                              "ms_min": min(region_ms), "ms_median": ms_total, "ms_max": max(region_ms)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "profiles/decode_attn_traffic.json (one ncu --set full capture)",
                          "kernel": "decode_attn_fp8_kernel<16,4>", "kernel_ms": kern_ms,
                          "algorithmic_bytes": alg, "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(),
                              "kind": "port",
-                             "sample": f"{nreq} of 64 requests, one pass, {cpu_dt:.2f} s",
+                             "sample": f"{nreq} of 64 requests, median of 3 passes after a warm-up, "
+                                       f"{cpu_dt:.2f} s per pass",
                              "gpu_vs_cpu_max_abs_err": cpu_err},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "note": "paged KV cache is device-resident engine state; per-step host inputs "
                             "(q, q scales, kv lengths, page table) staged in one pinned buffer, "
                             "one H2D copy; bf16 output read back"},
-            "gpu_launches": 3 * a.steps,
+            "gpu_launches": LAUNCHES_PER_STEP * a.steps,
             "clocks": clocks,
-        }))
+        }
+
+    # The headline numbers are final here. A watchdog prints the line if anything below hangs.
+    printed = threading.Event()
+
+    def emit():
+        if not printed.is_set():
+            printed.set()
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+
+    def watchdog():
+        if not printed.wait(EXTRA_BUDGET_S):
+            if line is not None:
+                line.setdefault("extra", {})["error"] = f"extra block exceeded {EXTRA_BUDGET_S} s; line emitted by watchdog"
+            emit()
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+
+    # free the decode tensors before the extras (the MoE weights alone are 22.6 GB)
+    del d, kc, vc, out, task_map, dev_buf, host_buf, y, args, keep
+    torch.cuda.empty_cache()
+
+    extra = {}
+    if not a.no_extra:
+        sys.path.insert(0, str(REPO / "tools"))
+        import bench_extras as bx
+
+        def leg(name, fn):
+            t0 = time.perf_counter()
+            try:
+                r = fn()
+                if isinstance(r, dict):
+                    r["wall_s"] = time.perf_counter() - t0
+                extra[name] = r
+            except Exception as ex:  # noqa: BLE001  (a failed leg is reported, not hidden)
+                extra[name] = {"error": repr(ex)[:400]}
+
+        if world == 1:
+            leg("moe_c3", lambda: bx.moe_c3(hpc, dev))
+            leg("prefill_c4_kv_per_tensor", lambda: bx.prefill_c4(hpc, dev, kpt=False))
+            leg("prefill_c4_k_per_token", lambda: bx.prefill_c4(hpc, dev, kpt=True))
+            leg("route_gemm", lambda: bx.route_gemm(hpc, dev))
+        leg("allreduce_c5", lambda: bx.allreduce_c5(hpc, dev, rank, world, dist))
+        extra["peaks"] = bx.peaks()
+    if rank == 0:
+        line["extra"] = extra
+    emit()
     if dist is not None:
-        dist.barrier()  # ranks > 0 wait for rank 0's CPU baseline instead of tearing NCCL down early
-        dist.destroy_process_group()
+        try:
+            dist.barrier()  # ranks > 0 wait for rank 0 instead of tearing NCCL down early
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+    sys.stdout.flush()
+    os._exit(0)  # symmetric-memory handles and NCCL teardown order must not turn a finished run into a hang
 
 
 if __name__ == "__main__":

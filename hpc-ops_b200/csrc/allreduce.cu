@@ -7,16 +7,27 @@
 //     fuse     : + residual -> residual_out (bf16), RMS over the row, * gamma
 //     broadcast: multimem.st of the normalised row into every rank's symmetric output buffer
 //                                                                 -- or P2P stores to every peer
-//   bracketed by a per-block cross-GPU signal-pad barrier (entry: all inputs written; exit: all
-//   outputs visible), CAS 0->1 post / 1->0 consume so that CUDA-graph replays are safe.
+//   Blocks are 256 threads holding one row as packed bf16 (4 x 16 B per thread at hidden 8192), several
+//   blocks per SM so that many rows are in flight per SM; the row-invariant gamma vectors are loaded
+//   once per block.
+//   Cross-GPU ordering is ONE rank-level barrier at entry and one at exit, built on monotonic epoch
+//   words in the signal pads (no CAS round trips, independent of the grid size, CUDA-graph replay
+//   safe because the epoch lives on the device): block 0 posts "rank r entered launch e" into every
+//   peer's pad, every block polls its OWN pad until all peers have posted; the last block to finish
+//   posts / awaits the exit epoch, so the kernel only completes once every peer's stores have landed.
 //
 // Low-latency path (replaces reference src/allreduce/fuse_allreduce_rmsnorm_low_latency.cu:16-453):
-//   Lamport two-shot in ONE kernel (the reference uses two, PDL-chained): token t is owned by rank
-//   t % W. Each rank scatters its row to the owner (P2P 16-B stores, -0.0 is the "not yet written"
-//   sentinel), the owner reduces the W rows in rank order and broadcasts the sum (multimem.st or
-//   P2P), every rank then adds the residual and normalises locally. Triple-buffered workspace with
-//   clear-ahead, state in `buffer_flags` exactly as laid out by the reference test
-//   (tests/test_fuse_allreduce_rmsnorm_low_latency.py:54-76).
+//   Lamport protocol (-0.0 = "not yet written"), triple-buffered workspace, state in `buffer_flags`
+//   as laid out by the reference test (tests/test_fuse_allreduce_rmsnorm_low_latency.py:54-76).
+//   two-shot (one kernel; the reference chains two with PDL): token t is owned by rank t % W; each
+//     rank scatters its row to the owner, the owner reduces the W rows in rank order and broadcasts
+//     the sum (multimem.st or P2P), every rank adds the residual and normalises locally.
+//   one-shot (small batches, when the workspace is large enough): every rank multicasts its row
+//     into slot [t][rank] of every rank's buffer, then reduces the W slots locally in rank order:
+//     one NVLink traversal instead of two.
+//   A call clears the buffer dirtied by the previous call, using the byte count that call recorded
+//   in buffer_flags[4] (the reference's clearDirtyLamportBuf bookkeeping), so batches of varying
+//   size never leave stale rows behind.
 #include "common.cuh"
 #include "host_utils.h"
 
@@ -24,57 +35,41 @@ namespace b200 {
 namespace ar {
 
 constexpr int kMaxRanks = 16;
-constexpr int kMaxVecPerThread = 4;  // 16-B vectors of a row held per thread
 
-// ---- system-scope signalling -----------------------------------------------------------------
-__device__ __forceinline__ uint32_t cas_sys_release(uint32_t* addr, uint32_t cmp, uint32_t val) {
-  uint32_t old;
-  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;"
-               : "=r"(old)
-               : "l"(addr), "r"(cmp), "r"(val)
-               : "memory");
-  return old;
-}
-__device__ __forceinline__ uint32_t cas_sys_acquire(uint32_t* addr, uint32_t cmp, uint32_t val) {
-  uint32_t old;
-  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;"
-               : "=r"(old)
-               : "l"(addr), "r"(cmp), "r"(val)
-               : "memory");
-  return old;
-}
+// ---- signal pad layout (uint32 words, zeroed when the symmetric buffer is created) ---------------
+constexpr int kPadEntry = 0;    // [0, 16)  : entry epoch posted by peer r
+constexpr int kPadExit = 16;    // [16, 32) : exit epoch posted by peer r
+constexpr int kPadEpoch = 32;   // local    : launches completed on this pad
+constexpr int kPadDone = 33;    // local    : blocks of the running launch that have finished
+
 #ifndef B200_AR_SPIN_LIMIT
 #define B200_AR_SPIN_LIMIT (1u << 28)
 #endif
-// Post "I arrived" into slot [block][my rank] of every peer's signal pad, then consume the W posts
-// in my own pad. signal_ptrs[r] = base of rank r's pad (uint32 slots). `phase` selects one of two
-// slot sets so that the entry and exit barriers of one launch never alias.
-__device__ __forceinline__ void block_barrier(uint64_t* const* signal_ptrs_unused,
-                                              const long long* signal_ptrs, int rank, int world,
-                                              int block, int nblocks, int phase) {
-  (void)signal_ptrs_unused;
-  __syncthreads();
-  if (threadIdx.x < world) {
-    const int peer = threadIdx.x;
-    const int slot_base = (phase * nblocks + block) * world;
-    uint32_t* post = reinterpret_cast<uint32_t*>(signal_ptrs[peer]) + slot_base + rank;
-    uint32_t spins = 0;
-    while (cas_sys_release(post, 0u, 1u) != 0u) {
-      if (++spins > B200_AR_SPIN_LIMIT) {
-        printf("allreduce barrier post timeout rank %d block %d peer %d\n", rank, block, peer);
-        __trap();
-      }
-    }
-    uint32_t* mine = reinterpret_cast<uint32_t*>(signal_ptrs[rank]) + slot_base + peer;
-    spins = 0;
-    while (cas_sys_acquire(mine, 1u, 0u) != 1u) {
-      if (++spins > B200_AR_SPIN_LIMIT) {
-        printf("allreduce barrier wait timeout rank %d block %d peer %d\n", rank, block, peer);
-        __trap();
-      }
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.global.release.sys.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.acquire.sys.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p has reached `target` (epochs are monotonic; compared modulo 2^32)
+__device__ __forceinline__ void wait_epoch(const uint32_t* p, uint32_t target, int rank, int peer,
+                                           const char* what) {
+  uint32_t spins = 0;
+  while (static_cast<int32_t>(ld_acquire_sys_u32(p) - target) < 0) {
+    if (++spins > B200_AR_SPIN_LIMIT) {
+      printf("allreduce %s barrier timeout: rank %d waits for peer %d (target %u)\n", what, rank,
+             peer, target);
+      __trap();
     }
   }
-  __syncthreads();
 }
 
 // ---- NVLS (multimem) 16-byte accesses ----------------------------------------------------------
@@ -136,59 +131,32 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return v;
 }
 
-__device__ __forceinline__ float block_sum(float v, float* smem, int nwarps) {
-  v = warp_sum_f32(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();  // smem reuse across rows
-  if (lane == 0) smem[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int w = 0; w < nwarps; w++) t += smem[w];
-  return t;
+// (reduced x + residual) -> bf16 (that is residual_out; the norm sees the rounded values);
+// returns the packed sum and accumulates its squares
+__device__ __forceinline__ uint4 add_residual(uint4 x, uint4 r, float& sq) {
+  float a[8], b[8];
+  unpack8(x, a);
+  unpack8(r, b);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] += b[i];
+  const uint4 packed = pack8(a);
+  unpack8(packed, a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) sq += a[i] * a[i];
+  return packed;
 }
-
-// residual add + RMSNorm of one row held as `nvec` 16-B vectors per thread.
-//   sum[] in : reduced x (float), out: nothing. Writes residual_out (bf16) and returns y vectors.
-__device__ __forceinline__ void fuse_row(float (*s)[8], int nvec, int vec0, int vstride, int nv_row,
-                                         const __nv_bfloat16* residual_row,
-                                         __nv_bfloat16* res_out_row, const __nv_bfloat16* weight,
-                                         float eps, int hidden, float* smem, int nwarps,
-                                         uint4* y_out) {
-  float sq = 0.f;
+// (x * rstd) rounded to bf16, then * gamma in bf16 (reference test rmsnorm():16-19)
+__device__ __forceinline__ uint4 normalise(uint4 x, uint4 gamma, float rstd) {
+  float a[8], w[8];
+  unpack8(x, a);
+  unpack8(gamma, w);
 #pragma unroll
-  for (int j = 0; j < kMaxVecPerThread; j++) {
-    const int v = vec0 + j * vstride;
-    if (j < nvec && v < nv_row) {
-      float r[8];
-      unpack8(ld_nc_v4(residual_row + v * 8), r);
-      float t[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) t[i] = s[j][i] + r[i];
-      const uint4 packed = pack8(t);  // residual_out is bf16; the norm sees the rounded values
-      *reinterpret_cast<uint4*>(res_out_row + v * 8) = packed;
-      unpack8(packed, s[j]);
-#pragma unroll
-      for (int i = 0; i < 8; i++) sq += s[j][i] * s[j][i];
-    }
-  }
-  const float tot = block_sum(sq, smem, nwarps);
-  const float rstd = rsqrtf(tot / static_cast<float>(hidden) + eps);
-#pragma unroll
-  for (int j = 0; j < kMaxVecPerThread; j++) {
-    const int v = vec0 + j * vstride;
-    if (j < nvec && v < nv_row) {
-      float w[8], n[8];
-      unpack8(ld_nc_v4(weight + v * 8), w);
-      // (x * rstd) rounded to bf16, then * gamma in bf16 (reference test rmsnorm():16-19)
-#pragma unroll
-      for (int i = 0; i < 8; i++) n[i] = __bfloat162float(__float2bfloat16_rn(s[j][i] * rstd)) * w[i];
-      y_out[j] = pack8(n);
-    }
-  }
+  for (int i = 0; i < 8; i++) a[i] = __bfloat162float(__float2bfloat16_rn(a[i] * rstd)) * w[i];
+  return pack8(a);
 }
 
 struct HtParams {
-  const __nv_bfloat16* x;        // local slice (used when world == 1)
+  const __nv_bfloat16* x;        // local slice
   const void* mc_x;              // multicast address of the slice, or NULL
   long long peer_x[kMaxRanks];   // P2P: every rank's slice address (when mc_x == NULL)
   const __nv_bfloat16* residual;
@@ -202,70 +170,75 @@ struct HtParams {
   float eps;
 };
 
-// reduce one row's vectors over the ranks (fp32) and fetch the matching residual vectors
-__device__ __forceinline__ void ht_load_row(const HtParams& p, int row, int nvec, int vstride,
-                                            int nv_row, float (*s)[8], uint4* res) {
-  const long long roff = static_cast<long long>(row) * p.hidden;
-#pragma unroll
-  for (int j = 0; j < kMaxVecPerThread; j++) {
-    const int v = threadIdx.x + j * vstride;
-    if (j < nvec && v < nv_row) {
-      if (p.world == 1) {
-        unpack8(ld_nc_v4(p.x + roff + v * 8), s[j]);
-      } else if (p.mc_x != nullptr) {
-        unpack8(multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8),
-                s[j]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[j][i] = 0.f;
-        for (int r = 0; r < p.world; r++) {
-          float t[8];
-          unpack8(ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[r]) + roff + v * 8), t);
-#pragma unroll
-          for (int i = 0; i < 8; i++) s[j][i] += t[i];
-        }
-      }
-      res[j] = ld_nc_v4(p.residual + roff + v * 8);
+template <int NVEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    ar_rmsnorm_ht_kernel(const HtParams p) {
+  constexpr int kWarps = THREADS / 32;
+  __shared__ float s_red[2][kWarps];
+  __shared__ uint32_t s_last;
+  const int nv_row = p.hidden / 8;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  uint32_t* pad = nullptr;
+  uint32_t epoch = 0;
+  if (p.world > 1) {
+    pad = reinterpret_cast<uint32_t*>(p.signal_ptrs[p.rank]);
+    epoch = ld_volatile_u32(pad + kPadEpoch);
+    if (blockIdx.x == 0 && tid < p.world) {
+      // release: this rank's input rows (written by earlier work on the stream) are visible
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(p.signal_ptrs[tid]) + kPadEntry + p.rank,
+                         2 * epoch + 1);
     }
   }
-}
+  // gamma is row-invariant: one load per block, overlapping the entry wait
+  uint4 wv[NVEC];
+#pragma unroll
+  for (int j = 0; j < NVEC; j++) {
+    const int v = tid + j * THREADS;
+    wv[j] = v < nv_row ? ld_nc_v4(p.weight + v * 8) : make_uint4(0, 0, 0, 0);
+  }
+  if (p.world > 1) {
+    if (tid < p.world) wait_epoch(pad + kPadEntry + tid, 2 * epoch + 1, p.rank, tid, "entry");
+    __syncthreads();
+  }
 
-template <int NVEC>
-__global__ void __launch_bounds__(1024)
-    ar_rmsnorm_ht_kernel(const HtParams p) {
-  __shared__ float s_red[2][32];
-  const int nv_row = p.hidden / 8;
-  const int vstride = blockDim.x;
-  const int nwarps = blockDim.x / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  if (p.world > 1) block_barrier(nullptr, p.signal_ptrs, p.rank, p.world, blockIdx.x, gridDim.x, 0);
-
-  // software pipeline over this block's rows: the (NVLS) loads of row i+1 are in flight while
-  // row i is normalised and broadcast
-  float s_cur[NVEC][8], s_nxt[NVEC][8];
-  uint4 r_cur[NVEC], r_nxt[NVEC];
-  int row = blockIdx.x;
-  if (row < p.num_tokens) ht_load_row(p, row, NVEC, vstride, nv_row, s_cur, r_cur);
   int it = 0;
-  for (; row < p.num_tokens; row += gridDim.x, it++) {
-    const int nrow = row + gridDim.x;
-    if (nrow < p.num_tokens) ht_load_row(p, nrow, NVEC, vstride, nv_row, s_nxt, r_nxt);
+  for (int row = blockIdx.x; row < p.num_tokens; row += gridDim.x, it++) {
     const long long roff = static_cast<long long>(row) * p.hidden;
+    uint4 xv[NVEC], rv[NVEC];
+#pragma unroll
+    for (int j = 0; j < NVEC; j++) {
+      const int v = tid + j * THREADS;
+      if (v < nv_row) {
+        if (p.world == 1) {
+          xv[j] = ld_nc_v4(p.x + roff + v * 8);
+        } else if (p.mc_x != nullptr) {
+          xv[j] = multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8);
+        } else {
+          // P2P: fp32 sum in rank order (deterministic), rounded to bf16 like the NVLS result
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc[i] = 0.f;
+#pragma unroll 4
+          for (int r = 0; r < p.world; r++) {
+            float t[8];
+            unpack8(ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[r]) + roff + v * 8), t);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] += t[i];
+          }
+          xv[j] = pack8(acc);
+        }
+        rv[j] = ld_nc_v4(p.residual + roff + v * 8);
+      }
+    }
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < NVEC; j++) {
-      const int v = threadIdx.x + j * vstride;
+      const int v = tid + j * THREADS;
       if (v < nv_row) {
-        float r[8], t[8];
-        unpack8(r_cur[j], r);
-#pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = s_cur[j][i] + r[i];
-        const uint4 packed = pack8(t);  // residual_out is bf16; the norm sees the rounded values
-        *reinterpret_cast<uint4*>(p.out_residual + roff + v * 8) = packed;
-        unpack8(packed, s_cur[j]);
-#pragma unroll
-        for (int i = 0; i < 8; i++) sq += s_cur[j][i] * s_cur[j][i];
+        xv[j] = add_residual(xv[j], rv[j], sq);
+        *reinterpret_cast<uint4*>(p.out_residual + roff + v * 8) = xv[j];
       }
     }
     sq = warp_sum_f32(sq);
@@ -273,19 +246,14 @@ __global__ void __launch_bounds__(1024)
     if (lane == 0) red[warp] = sq;
     __syncthreads();
     float tot = 0.f;
-    for (int w = 0; w < nwarps; w++) tot += red[w];
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) tot += red[w];
     const float rstd = rsqrtf(tot / static_cast<float>(p.hidden) + p.eps);
 #pragma unroll
     for (int j = 0; j < NVEC; j++) {
-      const int v = threadIdx.x + j * vstride;
+      const int v = tid + j * THREADS;
       if (v < nv_row) {
-        float w[8], n[8];
-        unpack8(ld_nc_v4(p.weight + v * 8), w);
-        // (x * rstd) rounded to bf16, then * gamma in bf16 (reference test rmsnorm():16-19)
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          n[i] = __bfloat162float(__float2bfloat16_rn(s_cur[j][i] * rstd)) * w[i];
-        const uint4 y = pack8(n);
+        const uint4 y = normalise(xv[j], wv[j], rstd);
         if (p.world == 1) {
           *reinterpret_cast<uint4*>(p.out_x + roff + v * 8) = y;
         } else if (p.mc_out_x != nullptr) {
@@ -297,27 +265,43 @@ __global__ void __launch_bounds__(1024)
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < NVEC; j++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) s_cur[j][i] = s_nxt[j][i];
-      r_cur[j] = r_nxt[j];
-    }
   }
+
   if (p.world > 1) {
-    __threadfence_system();
-    block_barrier(nullptr, p.signal_ptrs, p.rank, p.world, blockIdx.x, gridDim.x, 1);
+    __threadfence_system();  // this thread's broadcast stores have been performed system-wide
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(pad + kPadDone, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      // the whole rank is done: tell the peers, and do not finish before they all are
+      if (tid < p.world) {
+        __threadfence_system();
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(p.signal_ptrs[tid]) + kPadExit + p.rank,
+                           2 * epoch + 2);
+        wait_epoch(pad + kPadExit + tid, 2 * epoch + 2, p.rank, tid, "exit");
+      }
+      __syncthreads();
+      if (tid == 0) {
+        pad[kPadDone] = 0;
+        pad[kPadEpoch] = epoch + 1;
+        __threadfence();
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Low-latency Lamport two-shot, one kernel.
+// Low-latency Lamport path, one kernel.
 // workspace (per rank, symmetric): 3 buffers of `buf_bytes`; inside a buffer
-//   stage 0 (scatter)  : [ceil(T/W)][W][H] bf16   rows owned by this rank, one per source rank
-//   stage 1 (broadcast): [T_pad][H] bf16          reduced rows of all tokens
-// buffer_flags u32[9]: {cur, dirty, bytes_per_buffer, dirty_num_stages, clear[4], arrive_counter}
+//   two-shot  stage 0 (scatter)  : [ceil(T/W)][W][H] bf16   rows owned by this rank, one per source
+//             stage 1 (broadcast): [T][H] bf16              reduced rows of all tokens
+//   one-shot  [T][W][H] bf16                                every rank's row of every token
+// buffer_flags u32[9]: {cur, dirty, bytes_per_buffer, -, dirty_bytes, -, -, -, arrive_counter}
+//   cur   = buffer this call uses; dirty = buffer the previous call used (cleared by this call,
+//   for the `dirty_bytes` that call recorded).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kNegZero = 0x80000000u;
+constexpr long long kOneShotMaxBytes = 2ll << 20;  // per-rank receive volume up to which one-shot wins
 
 __device__ __forceinline__ bool vec_ready(uint4 v) {
   return v.x != kNegZero && v.y != kNegZero && v.z != kNegZero && v.w != kNegZero;
@@ -330,6 +314,18 @@ __device__ __forceinline__ uint4 scrub_neg_zero(uint4 v) {
   v.w = v.w == kNegZero ? 0u : v.w;
   return v;
 }
+__device__ __forceinline__ uint4 wait_vec(const uint8_t* src, int rank, int t, const char* what) {
+  uint4 d = ld_volatile_v4(src);
+  uint32_t spins = 0;
+  while (!vec_ready(d)) {
+    d = ld_volatile_v4(src);
+    if (++spins > B200_AR_SPIN_LIMIT) {
+      printf("allreduce LL %s timeout rank %d token %d\n", what, rank, t);
+      __trap();
+    }
+  }
+  return d;
+}
 
 struct LlParams {
   const __nv_bfloat16* x;          // local [T, H]
@@ -341,126 +337,180 @@ struct LlParams {
   __nv_bfloat16* out;
   __nv_bfloat16* out_residual;
   int rank, world, num_tokens, hidden;
+  int mode;                        // 0 = choose by size, 1 = force two-shot
   float eps;
 };
 
-__global__ void __launch_bounds__(1024)
+template <int NVEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
     ar_rmsnorm_ll_kernel(const LlParams p) {
-  __shared__ float s_red[32];
+  constexpr int kWarps = THREADS / 32;
+  __shared__ float s_red[2][kWarps];
   __shared__ uint32_t s_last;
   const int W = p.world;
   const int H = p.hidden;
   const int nv_row = H / 8;
-  const int vstride = blockDim.x;
-  const int nvec = (nv_row + vstride - 1) / vstride;
-  const int nwarps = blockDim.x / 32;
-  const uint32_t cur = p.flags[0];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t cur = p.flags[0] % 3u;
+  const uint32_t dirty = p.flags[1] % 3u;
   const uint32_t buf_bytes = p.flags[2];
-  const int tpr = (p.num_tokens + W - 1) / W;          // tokens per rank (owned)
-  const long long stage1_off = static_cast<long long>(tpr) * W * H * 2;  // bytes
+  const uint32_t dirty_bytes = p.flags[4];
+  const int tpr = (p.num_tokens + W - 1) / W;          // tokens per rank (owned), two-shot
+  const long long row_bytes = static_cast<long long>(H) * 2;
+  const long long stage1_off = static_cast<long long>(tpr) * W * row_bytes;
+  const long long one_shot_bytes = static_cast<long long>(p.num_tokens) * W * row_bytes;
+  const long long two_shot_bytes = stage1_off + static_cast<long long>(p.num_tokens) * row_bytes;
+  // identical on every rank (same T, W, H and workspace size)
+  const bool one_shot = p.mode == 0 && one_shot_bytes <= buf_bytes && one_shot_bytes <= kOneShotMaxBytes;
   const long long buf_off = static_cast<long long>(cur) * buf_bytes;
   uint8_t* my_ws = reinterpret_cast<uint8_t*>(p.peer_ws[p.rank]);
 
-  // clear-ahead: the buffer used two calls ago (every rank has finished with it)
-  {
-    const uint32_t clr = (cur + 1) % 3;
-    uint4 sent = make_uint4(kNegZero, kNegZero, kNegZero, kNegZero);
-    uint4* dst = reinterpret_cast<uint4*>(my_ws + static_cast<long long>(clr) * buf_bytes);
-    const long long nv = (stage1_off + static_cast<long long>(tpr) * W * H * 2) / 16;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  // clear the buffer the previous call dirtied (every rank has finished with it: that call
+  // completed only after all of its rows had arrived), for exactly the bytes it recorded
+  if (dirty != cur) {
+    const uint4 sent = make_uint4(kNegZero, kNegZero, kNegZero, kNegZero);
+    uint4* dst = reinterpret_cast<uint4*>(my_ws + static_cast<long long>(dirty) * buf_bytes);
+    const long long nv = (static_cast<long long>(dirty_bytes < buf_bytes ? dirty_bytes : buf_bytes) + 15) / 16;
+    for (long long i = static_cast<long long>(blockIdx.x) * THREADS + tid; i < nv;
+         i += static_cast<long long>(gridDim.x) * THREADS) {
       dst[i] = sent;
     }
   }
+  uint4 wv[NVEC];
+#pragma unroll
+  for (int j = 0; j < NVEC; j++) {
+    const int v = tid + j * THREADS;
+    wv[j] = v < nv_row ? ld_nc_v4(p.weight + v * 8) : make_uint4(0, 0, 0, 0);
+  }
 
-  for (int t = blockIdx.x; t < p.num_tokens; t += gridDim.x) {
-    const int owner = t % W;
-    const int lrow = t / W;
-    // ---- shot 1: my row of token t -> owner's stage-0 slot [lrow][rank] ----
-    {
-      uint8_t* dst = reinterpret_cast<uint8_t*>(p.peer_ws[owner]) + buf_off +
-                     (static_cast<long long>(lrow) * W + p.rank) * H * 2;
-      const __nv_bfloat16* src = p.x + static_cast<long long>(t) * H;
-      for (int v = threadIdx.x; v < nv_row; v += vstride) {
-        st_sys_v4(dst + v * 16, scrub_neg_zero(ld_nc_v4(src + v * 8)));
+  int it = 0;
+  for (int t = blockIdx.x; t < p.num_tokens; t += gridDim.x, it++) {
+    const long long roff = static_cast<long long>(t) * H;
+    uint4 xv[NVEC], rv[NVEC];
+#pragma unroll
+    for (int j = 0; j < NVEC; j++) {
+      const int v = tid + j * THREADS;
+      if (v < nv_row) {
+        xv[j] = scrub_neg_zero(ld_nc_v4(p.x + roff + v * 8));
+        rv[j] = ld_nc_v4(p.residual + roff + v * 8);
       }
     }
-    // ---- owner: reduce the W rows in rank order, broadcast the sum into stage 1 of every rank ----
-    if (owner == p.rank) {
-      const uint8_t* base = my_ws + buf_off + static_cast<long long>(lrow) * W * H * 2;
-      for (int v = threadIdx.x; v < nv_row; v += vstride) {
-        float acc[8];
+    if (one_shot) {
+      // ---- my row of token t -> slot [t][rank] of every rank ----
+      const long long off = buf_off + (static_cast<long long>(t) * W + p.rank) * row_bytes;
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = 0.f;
-        for (int r = 0; r < W; r++) {
-          const uint8_t* src = base + static_cast<long long>(r) * H * 2 + v * 16;
-          uint4 d = ld_volatile_v4(src);
-          uint32_t spins = 0;
-          while (!vec_ready(d)) {
-            d = ld_volatile_v4(src);
-            if (++spins > B200_AR_SPIN_LIMIT) {
-              printf("allreduce LL scatter timeout rank %d token %d src %d\n", p.rank, t, r);
-              __trap();
-            }
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) {
+          if (p.mc_ws != nullptr) {
+            multimem_st_v4(static_cast<uint8_t*>(p.mc_ws) + off + v * 16, xv[j]);
+          } else {
+            for (int r = 0; r < W; r++) st_sys_v4(reinterpret_cast<uint8_t*>(p.peer_ws[r]) + off + v * 16, xv[j]);
           }
-          float f[8];
-          unpack8(d, f);
-#pragma unroll
-          for (int i = 0; i < 8; i++) acc[i] += f[i];
         }
-        const uint4 sum = scrub_neg_zero(pack8(acc));
-        const long long off = buf_off + stage1_off + static_cast<long long>(t) * H * 2 + v * 16;
-        if (p.mc_ws != nullptr) {
-          multimem_st_v4(static_cast<uint8_t*>(p.mc_ws) + off, sum);
-        } else {
+      }
+      // ---- reduce the W slots of token t in rank order ----
+      const uint8_t* base = my_ws + buf_off + static_cast<long long>(t) * W * row_bytes;
+#pragma unroll
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) {
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc[i] = 0.f;
           for (int r = 0; r < W; r++) {
-            st_sys_v4(reinterpret_cast<uint8_t*>(p.peer_ws[r]) + off, sum);
+            float f[8];
+            unpack8(wait_vec(base + r * row_bytes + v * 16, p.rank, t, "one-shot"), f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] += f[i];
           }
+          xv[j] = pack8(acc);
         }
       }
-    }
-    // ---- shot 2 consumer: reduced row of token t, + residual, RMSNorm ----
-    {
-      const uint8_t* src = my_ws + buf_off + stage1_off + static_cast<long long>(t) * H * 2;
-      float s[kMaxVecPerThread][8];
+    } else {
+      const int owner = t % W;
+      const int lrow = t / W;
+      // ---- shot 1: my row of token t -> owner's stage-0 slot [lrow][rank] ----
+      {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.peer_ws[owner]) + buf_off +
+                       (static_cast<long long>(lrow) * W + p.rank) * row_bytes;
 #pragma unroll
-      for (int j = 0; j < kMaxVecPerThread; j++) {
-        const int v = threadIdx.x + j * vstride;
-        if (j < nvec && v < nv_row) {
-          uint4 d = ld_volatile_v4(src + v * 16);
-          uint32_t spins = 0;
-          while (!vec_ready(d)) {
-            d = ld_volatile_v4(src + v * 16);
-            if (++spins > B200_AR_SPIN_LIMIT) {
-              printf("allreduce LL broadcast timeout rank %d token %d\n", p.rank, t);
-              __trap();
+        for (int j = 0; j < NVEC; j++) {
+          const int v = tid + j * THREADS;
+          if (v < nv_row) st_sys_v4(dst + v * 16, xv[j]);
+        }
+      }
+      // ---- owner: reduce the W rows in rank order, broadcast the sum into stage 1 of every rank ----
+      if (owner == p.rank) {
+        const uint8_t* base = my_ws + buf_off + static_cast<long long>(lrow) * W * row_bytes;
+#pragma unroll
+        for (int j = 0; j < NVEC; j++) {
+          const int v = tid + j * THREADS;
+          if (v < nv_row) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = 0.f;
+            for (int r = 0; r < W; r++) {
+              float f[8];
+              unpack8(wait_vec(base + r * row_bytes + v * 16, p.rank, t, "scatter"), f);
+#pragma unroll
+              for (int i = 0; i < 8; i++) acc[i] += f[i];
+            }
+            const uint4 sum = scrub_neg_zero(pack8(acc));
+            const long long off = buf_off + stage1_off + static_cast<long long>(t) * row_bytes + v * 16;
+            if (p.mc_ws != nullptr) {
+              multimem_st_v4(static_cast<uint8_t*>(p.mc_ws) + off, sum);
+            } else {
+              for (int r = 0; r < W; r++) st_sys_v4(reinterpret_cast<uint8_t*>(p.peer_ws[r]) + off, sum);
             }
           }
-          unpack8(d, s[j]);
         }
       }
-      const long long roff = static_cast<long long>(t) * H;
-      uint4 y[kMaxVecPerThread];
-      fuse_row(s, nvec, threadIdx.x, vstride, nv_row, p.residual + roff, p.out_residual + roff,
-               p.weight, p.eps, H, s_red, nwarps, y);
+      // ---- shot 2 consumer: reduced row of token t ----
+      const uint8_t* src = my_ws + buf_off + stage1_off + static_cast<long long>(t) * row_bytes;
 #pragma unroll
-      for (int j = 0; j < kMaxVecPerThread; j++) {
-        const int v = threadIdx.x + j * vstride;
-        if (j < nvec && v < nv_row) *reinterpret_cast<uint4*>(p.out + roff + v * 8) = y[j];
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) xv[j] = wait_vec(src + v * 16, p.rank, t, "broadcast");
       }
+    }
+    // ---- + residual, RMSNorm ----
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NVEC; j++) {
+      const int v = tid + j * THREADS;
+      if (v < nv_row) {
+        xv[j] = add_residual(xv[j], rv[j], sq);
+        *reinterpret_cast<uint4*>(p.out_residual + roff + v * 8) = xv[j];
+      }
+    }
+    sq = warp_sum_f32(sq);
+    float* red = s_red[it & 1];
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) tot += red[w];
+    const float rstd = rsqrtf(tot / static_cast<float>(H) + p.eps);
+#pragma unroll
+    for (int j = 0; j < NVEC; j++) {
+      const int v = tid + j * THREADS;
+      if (v < nv_row) *reinterpret_cast<uint4*>(p.out + roff + v * 8) = normalise(xv[j], wv[j], rstd);
     }
   }
 
-  // last block out rotates the buffer index (replay-safe: state lives on the device)
+  // last block out rotates the buffers (replay-safe: the state lives on the device)
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     __threadfence();
     s_last = atomicAdd(&p.flags[8], 1u);
   }
   __syncthreads();
-  if (s_last == gridDim.x - 1 && threadIdx.x == 0) {
+  if (s_last == gridDim.x - 1 && tid == 0) {
     p.flags[8] = 0;
-    p.flags[1] = cur;            // dirty = the buffer just used
+    p.flags[1] = cur;            // dirty = the buffer just used ...
+    p.flags[4] = static_cast<uint32_t>(one_shot ? one_shot_bytes : two_shot_bytes);  // ... this far
     p.flags[0] = (cur + 1) % 3;  // next call
     __threadfence();
   }
@@ -471,13 +521,63 @@ __global__ void __launch_bounds__(1024)
 
 using namespace b200;  // NOLINT
 
-static int pick_threads(int hidden) {
+// block size / vectors per thread for a row of `hidden` bf16: 256-thread blocks holding up to 8
+// 16-B vectors per thread (hidden <= 16384), 1024 threads beyond that
+template <template <int, int> class L, typename P>
+static int dispatch_row_kernel(const P& p, int hidden, int grid, cudaStream_t stream) {
   const int nv = hidden / 8;
-  int th = (nv + 31) / 32 * 32;
-  if (th > 1024) th = 1024;
-  if (th < 64) th = 64;
+  if (nv <= 32) return L<1, 32>::run(p, grid, stream);
+  if (nv <= 64) return L<1, 64>::run(p, grid, stream);
+  if (nv <= 128) return L<1, 128>::run(p, grid, stream);
+  if (nv <= 256) return L<1, 256>::run(p, grid, stream);
+  if (nv <= 512) return L<2, 256>::run(p, grid, stream);
+  if (nv <= 1024) return L<4, 256>::run(p, grid, stream);
+  if (nv <= 2048) return L<8, 256>::run(p, grid, stream);
+  return L<4, 1024>::run(p, grid, stream);
+}
+static int row_threads(int hidden) {
+  const int nv = hidden / 8;
+  if (nv <= 32) return 32;
+  if (nv <= 64) return 64;
+  if (nv <= 128) return 128;
+  if (nv <= 2048) return 256;
+  return 1024;
+}
+// low-latency path: as many threads per row as there are vectors (one block per token, T is small)
+template <template <int, int> class L, typename P>
+static int dispatch_row_kernel_wide(const P& p, int hidden, int grid, cudaStream_t stream) {
+  const int nv = hidden / 8;
+  if (nv <= 32) return L<1, 32>::run(p, grid, stream);
+  if (nv <= 64) return L<1, 64>::run(p, grid, stream);
+  if (nv <= 128) return L<1, 128>::run(p, grid, stream);
+  if (nv <= 256) return L<1, 256>::run(p, grid, stream);
+  if (nv <= 512) return L<1, 512>::run(p, grid, stream);
+  if (nv <= 1024) return L<1, 1024>::run(p, grid, stream);
+  if (nv <= 2048) return L<2, 1024>::run(p, grid, stream);
+  return L<4, 1024>::run(p, grid, stream);
+}
+static int row_threads_wide(int hidden) {
+  const int nv = hidden / 8;
+  int th = 32;
+  while (th < nv && th < 1024) th *= 2;
   return th;
 }
+template <int NVEC, int THREADS>
+struct HtLaunch {
+  static int run(const ar::HtParams& p, int grid, cudaStream_t stream) {
+    ar::ar_rmsnorm_ht_kernel<NVEC, THREADS><<<grid, THREADS, 0, stream>>>(p);
+    HPC_CUDA_CHECK(cudaGetLastError());
+    return HPC_OK;
+  }
+};
+template <int NVEC, int THREADS>
+struct LlLaunch {
+  static int run(const ar::LlParams& p, int grid, cudaStream_t stream) {
+    ar::ar_rmsnorm_ll_kernel<NVEC, THREADS><<<grid, THREADS, 0, stream>>>(p);
+    HPC_CUDA_CHECK(cudaGetLastError());
+    return HPC_OK;
+  }
+};
 
 // replaces reference src/allreduce/fuse_allreduce_rmsnorm_high_throughput.h:12-18 (same arguments).
 // `signal_ptr` = device int64[world_size] of every rank's signal-pad address.
@@ -488,9 +588,8 @@ extern "C" int hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async(
     const int64_t* peer_input_ptrs_host, const int64_t* peer_output_ptrs_host, int64_t rank,
     int64_t world_size, int64_t num_max_blocks, double rms_norm_eps, int num_tokens,
     int hidden_size, cudaStream_t stream) {
-  HPC_REQUIRE(hidden_size % 8 == 0 && hidden_size > 0 && hidden_size <= 8 * 1024 * ar::kMaxVecPerThread,
-              "allreduce: hidden_size %d unsupported (multiple of 8, <= %d)", hidden_size,
-              8 * 1024 * ar::kMaxVecPerThread);
+  HPC_REQUIRE(hidden_size % 8 == 0 && hidden_size > 0 && hidden_size <= 32768,
+              "allreduce: hidden_size %d unsupported (multiple of 8, <= 32768)", hidden_size);
   HPC_REQUIRE(world_size >= 1 && world_size <= ar::kMaxRanks, "allreduce: world_size %lld",
               (long long)world_size);
   HPC_REQUIRE(rank >= 0 && rank < world_size, "allreduce: bad rank");
@@ -519,18 +618,19 @@ extern "C" int hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async(
   p.num_tokens = num_tokens;
   p.hidden = hidden_size;
   p.eps = static_cast<float>(rms_norm_eps);
-  // The grid must be identical on every rank (the barrier pairs block b with block b), so it
-  // depends only on num_max_blocks.
-  const int grid = static_cast<int>(num_max_blocks);
-  const int threads = pick_threads(hidden_size);
-  const int nvec = (hidden_size / 8 + threads - 1) / threads;
-  switch (nvec) {
-    case 1: ar::ar_rmsnorm_ht_kernel<1><<<grid, threads, 0, stream>>>(p); break;
-    case 2: ar::ar_rmsnorm_ht_kernel<2><<<grid, threads, 0, stream>>>(p); break;
-    default: ar::ar_rmsnorm_ht_kernel<4><<<grid, threads, 0, stream>>>(p); break;
+  // num_max_blocks is the caller's cap in units of full (1024-thread) CTAs, as in the reference;
+  // the barrier does not depend on the grid, so ranks may even use different grids. An empty slice
+  // still launches one block: the rank has to take part in the barriers.
+  const int threads = row_threads(hidden_size);
+  long long grid = static_cast<long long>(num_max_blocks) * (1024 / threads);
+  const long long resident = static_cast<long long>(sm_count()) * (threads >= 1024 ? 1 : 8);
+  if (grid > resident) grid = resident;
+  if (grid > num_tokens) grid = num_tokens;
+  if (grid < 1) {
+    if (world_size == 1) return HPC_OK;
+    grid = 1;
   }
-  HPC_CUDA_CHECK(cudaGetLastError());
-  return HPC_OK;
+  return dispatch_row_kernel<HtLaunch>(p, hidden_size, static_cast<int>(grid), stream);
 }
 
 extern "C" int hpc_fuse_allreduce_rmsnorm_high_throughput_async(
@@ -545,16 +645,20 @@ extern "C" int hpc_fuse_allreduce_rmsnorm_high_throughput_async(
 }
 
 // replaces reference src/allreduce/fuse_allreduce_rmsnorm_low_latency.h:29-49,503-504
-// (AllReduceFusionParams flattened into plain arguments).
-extern "C" int hpc_fuse_allreduce_rmsnorm_low_latency_async(
+// (AllReduceFusionParams flattened into plain arguments). `launch_with_pdl` is accepted for
+// signature compatibility (one kernel: nothing to chain); `num_max_blocks` <= 0 means "one block
+// per token up to the SM count". `protocol`: 0 = one-shot when the batch is small and the workspace
+// holds [T][W][H] (decided on the device, identically on every rank), 1 = always two-shot.
+extern "C" int hpc_fuse_allreduce_rmsnorm_low_latency_ex_async(
     int n_ranks, int rank, int num_tokens, int token_dim, void** buffer_ptrs_dev,
     void* buffer_ptr_local, void* multicast_ptr, uint32_t* buffer_flags, int rmsnorm_fusion,
     int launch_with_pdl, const void* input, const void* residual_in, const void* gamma,
-    double epsilon, void* residual_out, void* output, int num_max_blocks, cudaStream_t stream) {
+    double epsilon, void* residual_out, void* output, int num_max_blocks, int protocol,
+    cudaStream_t stream) {
   (void)buffer_ptr_local;
   (void)launch_with_pdl;
   HPC_REQUIRE(rmsnorm_fusion, "allreduce LL: only the fused RMSNorm mode is implemented");
-  HPC_REQUIRE(token_dim % 8 == 0 && token_dim > 0 && token_dim <= 8 * 1024 * ar::kMaxVecPerThread,
+  HPC_REQUIRE(token_dim % 8 == 0 && token_dim > 0 && token_dim <= 32768,
               "allreduce LL: hidden_size %d unsupported", token_dim);
   HPC_REQUIRE(n_ranks >= 1 && n_ranks <= ar::kMaxRanks && rank >= 0 && rank < n_ranks,
               "allreduce LL: bad rank/world");
@@ -573,13 +677,25 @@ extern "C" int hpc_fuse_allreduce_rmsnorm_low_latency_async(
   p.world = n_ranks;
   p.num_tokens = num_tokens;
   p.hidden = token_dim;
+  p.mode = protocol;
   p.eps = static_cast<float>(epsilon);
   // every token needs its block to be resident on all ranks at about the same time: the loop is
   // in increasing token order on every rank, so any grid size is deadlock-free
-  int grid = num_tokens;
-  const int cap = num_max_blocks > 0 ? num_max_blocks : sm_count();
+  const int threads = row_threads_wide(token_dim);
+  long long grid = num_tokens;
+  const long long cap = num_max_blocks > 0 ? static_cast<long long>(num_max_blocks) * (1024 / threads)
+                                           : static_cast<long long>(sm_count()) * (threads >= 1024 ? 1 : 2);
   if (grid > cap) grid = cap;
-  ar::ar_rmsnorm_ll_kernel<<<grid, pick_threads(token_dim), 0, stream>>>(p);
-  HPC_CUDA_CHECK(cudaGetLastError());
-  return HPC_OK;
+  return dispatch_row_kernel_wide<LlLaunch>(p, token_dim, static_cast<int>(grid), stream);
+}
+
+extern "C" int hpc_fuse_allreduce_rmsnorm_low_latency_async(
+    int n_ranks, int rank, int num_tokens, int token_dim, void** buffer_ptrs_dev,
+    void* buffer_ptr_local, void* multicast_ptr, uint32_t* buffer_flags, int rmsnorm_fusion,
+    int launch_with_pdl, const void* input, const void* residual_in, const void* gamma,
+    double epsilon, void* residual_out, void* output, int num_max_blocks, cudaStream_t stream) {
+  return hpc_fuse_allreduce_rmsnorm_low_latency_ex_async(
+      n_ranks, rank, num_tokens, token_dim, buffer_ptrs_dev, buffer_ptr_local, multicast_ptr,
+      buffer_flags, rmsnorm_fusion, launch_with_pdl, input, residual_in, gamma, epsilon,
+      residual_out, output, num_max_blocks, 1, stream);
 }

@@ -63,6 +63,7 @@ struct Params {
   int scale_tile;  // column padding granule of the transposed activation-scale layout
   int use_bf16_mul;
   int* tile_counter;  // dynamic tile scheduler (zeroed by the launcher)
+  int debug;  // HPC_B200_MOE_DEBUG diagnostics (timing experiments only; results are wrong when set)
 };
 
 __device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float2 f) {
@@ -327,6 +328,20 @@ __global__ void __launch_bounds__(kThreads, 1)
                               crank == 0 ? nrow0 : nrow1, t.g, static_cast<uint16_t>(3));
           } else {
             mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+            if (p.debug & 3) {  // diagnostics: leave out the weight (1) / activation (2) tile loads
+              const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes);
+              if (bytes == 0) {
+                mbar_arrive(&full[s]);
+              } else {
+                mbar_arrive_expect_tx(&full[s], bytes);
+              }
+              if (!(p.debug & 2)) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+              if (!(p.debug & 1)) {
+                tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
+                tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+              }
+              continue;
+            }
             mbar_arrive_expect_tx(&full[s], kStageBytes);
             tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
             tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
@@ -448,6 +463,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t buf = acc_it & 1;
           mbar_wait(&part_full[buf], (acc_it >> 1) & 1);
           tc_fence_after();
+          if (p.debug & 4) {  // diagnostics: no TMEM drain / promotion
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&part_empty[buf]);
+            continue;
+          }
           const float f0 = xs * w0, f1 = xs * w1;
           const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1);
           const uint32_t base = lane_addr + buf * kBN + wg * 64;
@@ -609,6 +630,11 @@ static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Param
     configured[dev] = true;
   }
   Params pp = p;
+  static const int dbg = [] {
+    const char* e = std::getenv("HPC_B200_MOE_DEBUG");
+    return e ? std::atoi(e) : 0;
+  }();
+  pp.debug = dbg;
   pp.tile_counter = launch_counter(stream);  // dynamic tile scheduler
   if (pp.tile_counter == nullptr) return HPC_ERR_CUDA;
   if constexpr (kCluster) {

