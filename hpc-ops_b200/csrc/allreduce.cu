@@ -170,7 +170,8 @@ struct HtParams {
   float eps;
 };
 
-template <int NVEC, int THREADS>
+// kMode: 0 = single rank (pure residual + RMSNorm), 1 = NVLS multimem, 2 = P2P loads / stores
+template <int NVEC, int THREADS, int kMode>
 __global__ void __launch_bounds__(THREADS)
     ar_rmsnorm_ht_kernel(const HtParams p) {
   constexpr int kWarps = THREADS / 32;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(THREADS)
 
   uint32_t* pad = nullptr;
   uint32_t epoch = 0;
-  if (p.world > 1) {
+  if constexpr (kMode != 0) {
     pad = reinterpret_cast<uint32_t*>(p.signal_ptrs[p.rank]);
     epoch = ld_volatile_u32(pad + kPadEpoch);
     if (blockIdx.x == 0 && tid < p.world) {
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(THREADS)
     const int v = tid + j * THREADS;
     wv[j] = v < nv_row ? ld_nc_v4(p.weight + v * 8) : make_uint4(0, 0, 0, 0);
   }
-  if (p.world > 1) {
+  if constexpr (kMode != 0) {
     if (tid < p.world) wait_epoch(pad + kPadEntry + tid, 2 * epoch + 1, p.rank, tid, "entry");
     __syncthreads();
   }
@@ -210,27 +211,59 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int j = 0; j < NVEC; j++) {
       const int v = tid + j * THREADS;
-      if (v < nv_row) {
-        if (p.world == 1) {
-          xv[j] = ld_nc_v4(p.x + roff + v * 8);
-        } else if (p.mc_x != nullptr) {
-          xv[j] = multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8);
-        } else {
-          // P2P: fp32 sum in rank order (deterministic), rounded to bf16 like the NVLS result
-          float acc[8];
+      if (v < nv_row) rv[j] = ld_nc_v4(p.residual + roff + v * 8);
+    }
+    if constexpr (kMode == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) acc[i] = 0.f;
-#pragma unroll 4
-          for (int r = 0; r < p.world; r++) {
-            float t[8];
-            unpack8(ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[r]) + roff + v * 8), t);
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] += t[i];
-          }
-          xv[j] = pack8(acc);
-        }
-        rv[j] = ld_nc_v4(p.residual + roff + v * 8);
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) xv[j] = ld_nc_v4(p.x + roff + v * 8);
       }
+    } else if constexpr (kMode == 1) {
+#pragma unroll
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) {
+          xv[j] = multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8);
+        }
+      }
+    } else {
+      // P2P: fp32 sum in rank order (deterministic), rounded to bf16 like the NVLS result. The
+      // loads of two ranks x NVEC vectors are issued before any is consumed: a peer load takes
+      // ~1 us, so the bytes in flight per thread decide the link utilisation.
+      float acc[NVEC][8];
+#pragma unroll
+      for (int j = 0; j < NVEC; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[j][i] = 0.f;
+      for (int r0 = 0; r0 < p.world; r0 += 2) {
+        uint4 raw[2][NVEC];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+          for (int j = 0; j < NVEC; j++) {
+            const int v = tid + j * THREADS;
+            if (r0 + rr < p.world && v < nv_row) {
+              raw[rr][j] = ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[r0 + rr]) + roff + v * 8);
+            }
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+          for (int j = 0; j < NVEC; j++) {
+            const int v = tid + j * THREADS;
+            if (r0 + rr < p.world && v < nv_row) {
+              float t[8];
+              unpack8(raw[rr][j], t);
+#pragma unroll
+              for (int i = 0; i < 8; i++) acc[j][i] += t[i];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NVEC; j++) xv[j] = pack8(acc[j]);
     }
     float sq = 0.f;
 #pragma unroll
@@ -254,9 +287,9 @@ __global__ void __launch_bounds__(THREADS)
       const int v = tid + j * THREADS;
       if (v < nv_row) {
         const uint4 y = normalise(xv[j], wv[j], rstd);
-        if (p.world == 1) {
+        if constexpr (kMode == 0) {
           *reinterpret_cast<uint4*>(p.out_x + roff + v * 8) = y;
-        } else if (p.mc_out_x != nullptr) {
+        } else if constexpr (kMode == 1) {
           multimem_st_v4(static_cast<__nv_bfloat16*>(p.mc_out_x) + roff + v * 8, y);
         } else {
           for (int r = 0; r < p.world; r++) {
@@ -267,7 +300,7 @@ __global__ void __launch_bounds__(THREADS)
     }
   }
 
-  if (p.world > 1) {
+  if constexpr (kMode != 0) {
     __threadfence_system();  // this thread's broadcast stores have been performed system-wide
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(pad + kPadDone, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -565,7 +598,13 @@ static int row_threads_wide(int hidden) {
 template <int NVEC, int THREADS>
 struct HtLaunch {
   static int run(const ar::HtParams& p, int grid, cudaStream_t stream) {
-    ar::ar_rmsnorm_ht_kernel<NVEC, THREADS><<<grid, THREADS, 0, stream>>>(p);
+    if (p.world == 1) {
+      ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 0><<<grid, THREADS, 0, stream>>>(p);
+    } else if (p.mc_x != nullptr) {
+      ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 1><<<grid, THREADS, 0, stream>>>(p);
+    } else {
+      ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 2><<<grid, THREADS, 0, stream>>>(p);
+    }
     HPC_CUDA_CHECK(cudaGetLastError());
     return HPC_OK;
   }

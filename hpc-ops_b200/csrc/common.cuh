@@ -72,6 +72,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (PDL). A kernel launched with the programmatic-stream-serialization
+// attribute may begin while its predecessor in the stream is still running: everything before
+// pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail;
+// pdl_wait() returns once the predecessor has completed and its writes are visible. Every kernel of
+// this library waits before its first access to global memory, so chains stay correct with or
+// without the attribute. pdl_launch_dependents() lets the successor's CTAs be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // 16-byte streaming global accesses
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;

@@ -169,6 +169,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // PDL: all of the above overlapped the tail of the previous kernel (the task-map assign); from
+  // here on its output is read. The combine kernel's CTAs may be scheduled now: they park at
+  // their own pdl_wait() until this grid has completed.
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int ntpc1 = p.task_map[0];
   const int* bin = p.task_map + (1 + static_cast<long long>(blockIdx.x) * ntpc1) * kTaskStride;
 
@@ -478,6 +484,9 @@ __global__ void __launch_bounds__(128)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_wait();               // the attention kernel's partials and LSEs are complete
+  pdl_launch_dependents();  // whatever follows may set itself up
+
   const int ntpc1 = task_map[0];
   const int nctas = task_map[1];
   const int max_batch = task_map[3];
@@ -548,8 +557,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured[dev] = true;
   }
-  kern<<<grid, kThreads, L::kTotal, stream>>>(tq, tk, tv, p);
-  HPC_CUDA_CHECK(cudaGetLastError());
+  HPC_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), L::kTotal, stream, 1, tq, tk, tv, p));
   return HPC_OK;
 }
 
@@ -597,11 +605,11 @@ static int decode_fp8_impl(
   const int lse_pad_ = (group + 7) / 8 * 8;
   if (run_combine && !run_attn) {
     const int out_rows_ = num_batch * num_seq_q * num_head_q;
-    decode::decode_combine_kernel<<<out_rows_, 128, 0, stream>>>(
-        static_cast<__nv_bfloat16*>(y_ptr), static_cast<const float*>(split_out_ptr),
-        static_cast<const float*>(lse_ptr), task_map_ptr, num_batch, num_seq_q, num_head_q,
-        num_head_k, group, splitk, lse_pad_, ldY);
-    HPC_CUDA_CHECK(cudaGetLastError());
+    HPC_CUDA_CHECK(launch_pdl(decode::decode_combine_kernel, dim3(out_rows_), dim3(128), 0, stream, 1,
+                              static_cast<__nv_bfloat16*>(y_ptr),
+                              static_cast<const float*>(split_out_ptr),
+                              static_cast<const float*>(lse_ptr), task_map_ptr, num_batch, num_seq_q,
+                              num_head_q, num_head_k, group, splitk, lse_pad_, ldY));
     return HPC_OK;
   }
 
@@ -706,10 +714,10 @@ static int decode_fp8_impl(
   if (!run_combine) return HPC_OK;
 
   const int out_rows = num_batch * num_seq_q * num_head_q;
-  decode::decode_combine_kernel<<<out_rows, 128, 0, stream>>>(
-      static_cast<__nv_bfloat16*>(y_ptr), p.split_out, p.lse, task_map_ptr, num_batch, num_seq_q,
-      num_head_q, num_head_k, group, splitk, p.lse_pad, ldY);
-  HPC_CUDA_CHECK(cudaGetLastError());
+  HPC_CUDA_CHECK(launch_pdl(decode::decode_combine_kernel, dim3(out_rows), dim3(128), 0, stream, 1,
+                            static_cast<__nv_bfloat16*>(y_ptr), static_cast<const float*>(p.split_out),
+                            static_cast<const float*>(p.lse), task_map_ptr, num_batch, num_seq_q,
+                            num_head_q, num_head_k, group, splitk, p.lse_pad, ldY));
   return HPC_OK;
 }
 

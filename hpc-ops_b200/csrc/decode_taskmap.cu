@@ -187,6 +187,11 @@ __global__ void __launch_bounds__(kThreads)
   const int warp = tid >> 5;
   const int icta = blockIdx.x;
 
+  // PDL: the previous kernel in the stream (e.g. the last step's combine) may still be reading the
+  // task map this kernel rewrites; the next kernel (attention) may set itself up meanwhile
+  pdl_wait();
+  pdl_launch_dependents();
+
   // ---- per-batch tile counts + block-wide exclusive scan (tiles and non-empty count) ----
   int loc_tiles[kItems];
   int loc_nz[kItems];
@@ -443,9 +448,8 @@ extern "C" int hpc_assign_attention_decode_task_async(int* task_map, const int* 
               "assign_attention_decode_task: batch %d outside (0, %d]", num_batch, kMaxNumBatch);
   HPC_REQUIRE(tilen == 64 || tilen == 128, "tilen must be 64 or 128, got %d", tilen);
   HPC_REQUIRE(num_total_ctas > 0 && num_head_kv > 0, "bad task-map geometry");
-  assign_task_kernel<<<num_total_ctas, kThreads, 0, stream>>>(
-      task_map, num_seq_kvcache, num_batch, num_head_kv, num_seq_q, new_kv_included,
-      min_process_len, num_total_ctas, tilen);
-  HPC_CUDA_CHECK(cudaGetLastError());
+  HPC_CUDA_CHECK(launch_pdl(assign_task_kernel, dim3(num_total_ctas), dim3(kThreads), 0, stream, 1,
+                            task_map, num_seq_kvcache, num_batch, num_head_kv, num_seq_q,
+                            new_kv_included, min_process_len, num_total_ctas, tilen));
   return HPC_OK;
 }

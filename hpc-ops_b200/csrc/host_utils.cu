@@ -1,5 +1,6 @@
 #include "host_utils.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -25,6 +26,14 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("HPC_B200_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int device_slot() {

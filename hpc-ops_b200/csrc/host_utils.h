@@ -33,6 +33,8 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();
+// HPC_B200_PDL=0 turns programmatic dependent launch off (plain stream order), default on.
+bool pdl_enabled();
 // Current CUDA device clamped to [0, 63] (0 when the runtime is unavailable). Launchers keep their
 // one-time state (function attributes, scratch pools) per device: one process may drive several GPUs.
 int device_slot();
@@ -51,5 +53,35 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, con
                 int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                 CUtensorMapSwizzle swizzle,
                 CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+
+// Launch `kern` so that it may start before the previous kernel in `stream` has finished
+// (programmatic dependent launch; the kernel calls pdl_wait() before touching global memory).
+// `cluster_x` > 1 additionally launches thread-block clusters of that size.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    n++;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    n++;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace b200

@@ -584,12 +584,6 @@ static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, cons
   p.v_head_first = vhf;
   p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(128.f);
 
-  static const bool wg2 = [] {
-    const char* e = std::getenv("HPC_B200_PREFILL_WG2");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (wg2) return prefill_wg2_launch(k_per_token, tq, tk, tv, p, stream);  // experimental variant
-
   const int grid = 2 * sm_count();  // two resident CTAs per SM
   // share of exponentials on the FMA pipe: HPC_B200_PREFILL_POLY = 0 | 2 | 4 (per 8 scores)
   static const int poly = [] {

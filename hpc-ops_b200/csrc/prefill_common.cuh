@@ -96,7 +96,3 @@ __device__ __forceinline__ void exp2_poly_pair(const uint64_t x2, float& e0, flo
 
 }  // namespace prefill
 }  // namespace b200
-
-// experimental two-softmax-warpgroup variant (prefill_blocksparse_fp8_wg2.cu), HPC_B200_PREFILL_WG2=1
-int prefill_wg2_launch(bool k_per_token, const CUtensorMap& tq, const CUtensorMap& tk,
-                       const CUtensorMap& tv, const b200::prefill::Params& p, cudaStream_t stream);
