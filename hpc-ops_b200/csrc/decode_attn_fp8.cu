@@ -53,6 +53,9 @@ struct Params {
   int k_head_first;  // TMA dim order of the cache maps: (d, head, token, blk) or (d, token, head, blk)
   int v_head_first;
   float softmax_scale_log2;
+  // k-per-token variant: in-cache scale rows: float index
+  //   blk * ks_blk + (t / 32) * ks_row + head * ks_head + t % 32     (t = token slot in the page)
+  long long ks_blk, ks_row, ks_head;
 };
 
 struct Task {
@@ -105,7 +108,10 @@ struct Smem {
 // No "empty" barriers are needed for S, P and O: the MMA thread issues QK(n) only after it has
 // waited p_full(n-2) (softmax threads arrive on it after their tcgen05.ld of S(n-2) and O(n-3)),
 // and a softmax thread writes P(n) only after it has consumed O(n-2), i.e. PV(n-2) completed.
-template <int NQ, int RL>
+// kKPerToken: q per-token/head, k per-token/head (scales in the cache's extra rows), v per-head
+// (reference .../smallm_fp8_qkpertoken_perhead_vperhead_dim128_dynamic_splitk_kernels.cuh:29);
+// otherwise q per-token/head, k/v per-tensor.
+template <int NQ, int RL, bool kKPerToken>
 __global__ void __launch_bounds__(kThreads, 1)
     decode_attn_fp8_kernel(const __grid_constant__ CUtensorMap tmap_q,
                            const __grid_constant__ CUtensorMap tmap_k,
@@ -294,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row_in_tile = quad * 32 + lane;  // key index (S^T) and d index (O^T)
     const int sw = warp - 2;             // 0..3 index for smem exchange
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const float kscale = p.kscale[0];
-    const float out_scale = p.vscale[0] * (1.0f / 256.0f);
+    const float kscale = kKPerToken ? 1.f : p.kscale[0];
+    float out_scale = kKPerToken ? 0.f : p.vscale[0] * (1.0f / 256.0f);
 
     uint32_t n = 0;
     Task t;
@@ -322,6 +328,25 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int lim_len = t.num_seqkv;
       const int lim_causal = t.num_seqkvcache;
       const int ntiles = t.num_tile_kv;
+      // k-per-token: this thread's key of tile tt sits in page (2 tt + row / 64) of the task's
+      // page list; its scale is fetched one tile ahead
+      const int* page_ids = p.block_ids + static_cast<long long>(t.ibatch) * p.num_seq_max_blocks +
+                            t.iseq_start / kPage;
+      const int npages = (t.num_seqkv + kPage - 1) / kPage;
+      auto key_scale = [&](int tile) -> float {
+        int pg = 2 * tile + (row_in_tile >> 6);
+        pg = pg < npages ? pg : npages - 1;
+        if (pg < 0) return 0.f;
+        const long long blk = __ldg(page_ids + pg);
+        const int slot = row_in_tile & 63;
+        return __ldg(p.kscale + blk * p.ks_blk + (slot >> 5) * p.ks_row + t.ihead_kv * p.ks_head +
+                     (slot & 31));
+      };
+      float ks_next = 1.f;
+      if constexpr (kKPerToken) {
+        out_scale = __ldg(p.vscale + t.ihead_kv) * (1.0f / 256.0f);
+        ks_next = ntiles > 0 ? key_scale(0) : 0.f;
+      }
 
       auto consume_o = [&](uint32_t m) {
         const uint32_t buf = m & 1;
@@ -343,6 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int tt = 0; tt < ntiles; tt++) {
         const uint32_t buf = n & 1;
         const uint32_t ph = (n >> 1) & 1;
+        const float ks_cur = ks_next;
+        if constexpr (kKPerToken) {
+          if (tt + 1 < ntiles) ks_next = key_scale(tt + 1);
+        }
         mbar_wait(&s_full[buf], ph);
         tc_fence_after();
         uint32_t sraw[NQ];
@@ -361,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int r = 0; r < RL; r++) {
           float v = __uint_as_float(sraw[r]) * c[r];
+          if constexpr (kKPerToken) v *= ks_cur;
           if (need_mask) {
             const int sq = r / p.group;
             const bool dead = (key >= lim_len) || (key > lim_causal + sq);
@@ -545,11 +575,11 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-template <int NQ, int RL>
+template <int NQ, int RL, bool kKPerToken>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const Params& p, int grid, cudaStream_t stream) {
   using L = Smem<NQ>;
-  auto kern = decode_attn_fp8_kernel<NQ, RL>;
+  auto kern = decode_attn_fp8_kernel<NQ, RL, kKPerToken>;
   static bool configured[64] = {false};
   const int dev = device_slot();
   if (!configured[dev]) {
@@ -581,10 +611,20 @@ static int decode_fp8_impl(
   (void)new_kv_included;
   (void)splitk_min_len;
   (void)consumers;
-  HPC_REQUIRE(quant_type == 1,
-              "attention_decode_fp8: only quant_type 1 (q per-token/head, k/v per-tensor) is "
-              "implemented in this build, got %d",
+  // quant_type (reference hpc/attention.py QuantType): 0 = q,k per token/head + v per head,
+  // 1 = q per token/head + k,v per tensor
+  HPC_REQUIRE(quant_type == 0 || quant_type == 1,
+              "attention_decode_fp8: quant_type %d is not implemented (0: q/k per token-head, v per "
+              "head; 1: q per token-head, k/v per tensor)",
               quant_type);
+  if (quant_type == 0) {
+    // the per-token k scales live in the cache allocation's extra rows and share its strides
+    // (reference src/attention/entry.cc:245-253): float strides = byte strides / 4
+    HPC_REQUIRE((kcache_block_stride % 4) == 0 && (kcache_token_stride % 4) == 0 &&
+                    (kcache_head_stride % 4) == 0 && kscale_ptr != nullptr &&
+                    (reinterpret_cast<uintptr_t>(kscale_ptr) & 3) == 0,
+                "attention_decode_fp8: k scale rows must be 4-byte aligned slices of the cache");
+  }
   HPC_REQUIRE(task_map_ptr != nullptr, "attention_decode_fp8: a task_map is required on sm_100");
   HPC_REQUIRE(num_dim_qk == 128 && num_dim_v == 128, "head dim must be 128");
   HPC_REQUIRE(block_size == 64, "kvcache paged blocksize must be 64");
@@ -694,22 +734,29 @@ static int decode_fp8_impl(
   p.k_head_first = k_head_first;
   p.v_head_first = v_head_first;
   p.softmax_scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(num_dim_qk));
+  p.ks_blk = kcache_block_stride / 4;
+  p.ks_row = kcache_token_stride / 4;
+  p.ks_head = kcache_head_stride / 4;
 
   const int grid = splitk;  // == num_total_ctas of the task map
   int rc;
+#define HPC_DECODE_LAUNCH(NQ_, RL_)                                                   \
+  rc = (quant_type == 0) ? decode::launch_attn<NQ_, RL_, true>(tq, tk, tv, p, grid, stream) \
+                         : decode::launch_attn<NQ_, RL_, false>(tq, tk, tv, p, grid, stream)
   if (rows <= 4) {
-    rc = decode::launch_attn<16, 4>(tq, tk, tv, p, grid, stream);
+    HPC_DECODE_LAUNCH(16, 4);
   } else if (rows <= 8) {
-    rc = decode::launch_attn<16, 8>(tq, tk, tv, p, grid, stream);
+    HPC_DECODE_LAUNCH(16, 8);
   } else if (rows <= 12) {
-    rc = decode::launch_attn<16, 12>(tq, tk, tv, p, grid, stream);
+    HPC_DECODE_LAUNCH(16, 12);
   } else if (rows <= 16) {
-    rc = decode::launch_attn<16, 16>(tq, tk, tv, p, grid, stream);
+    HPC_DECODE_LAUNCH(16, 16);
   } else if (rows <= 24) {
-    rc = decode::launch_attn<32, 24>(tq, tk, tv, p, grid, stream);
+    HPC_DECODE_LAUNCH(32, 24);
   } else {
-    rc = decode::launch_attn<32, 32>(tq, tk, tv, p, grid, stream);
+    HPC_DECODE_LAUNCH(32, 32);
   }
+#undef HPC_DECODE_LAUNCH
   if (rc) return rc;
   if (!run_combine) return HPC_OK;
 

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
                      int* __restrict__ counts, int total, int num_expert_local, int expert_base) {
   __shared__ int hist[kMaxExperts];
   for (int i = threadIdx.x; i < num_expert_local; i += blockDim.x) hist[i] = 0;
+  pdl_wait();  // PDL: whatever ran before on the stream may still be producing topk_ids
+  pdl_launch_dependents();
   __syncthreads();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int e = topk_ids[idx] - expert_base;
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(kRouteThreads)
   const int lane = tid & 31;
   const int nwarps = kRouteThreads / 32;
 
+  pdl_wait();  // the histogram is complete
+  pdl_launch_dependents();
   if (warp == 0) {
     // exclusive scans over the experts: rows and scale columns (padded to scale_tile)
     int carry = 0, carry_pad = 0, carry_tiles = 0;
@@ -148,6 +152,8 @@ __global__ void __launch_bounds__(256)
                       int num_topk) {
   const int vec_per_row = hidden / 8;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_wait();  // the Down GEMM's rows are complete
+  pdl_launch_dependents();
   if (gid >= static_cast<long long>(num_tokens) * vec_per_row) return;
   const int t = static_cast<int>(gid / vec_per_row);
   const int v = static_cast<int>(gid % vec_per_row);
@@ -206,11 +212,13 @@ static int route(const void* x, const float* x_scale, void* gathered, float* xs_
   moe_count_kernel<<<grid, 256, 0, stream>>>(topk_ids, topk_pos, counts, total, num_expert_local,
                                              expert_base);
   HPC_CUDA_CHECK(cudaGetLastError());
-  moe_route_gather_kernel<<<num_expert_local, kRouteThreads, 0, stream>>>(
-      static_cast<const uint8_t*>(x), x_scale, topk_ids, counts, static_cast<uint8_t*>(gathered),
-      xs_t, topk_pos, cu_tokens, tiles, cu_tiles, num_tokens, num_topk, hidden, num_expert_local,
-      expert_base, scale_tile, m_pad);
-  HPC_CUDA_CHECK(cudaGetLastError());
+  // from here on the pipeline is a PDL chain (as the reference chains its MoE stages,
+  // src/fuse_moe/fuse_moe.cu:71-116): route/gather -> Gate-Up GEMM -> Down GEMM -> reduce
+  HPC_CUDA_CHECK(launch_pdl(moe_route_gather_kernel, dim3(num_expert_local), dim3(kRouteThreads), 0,
+                            stream, 1, static_cast<const uint8_t*>(x), x_scale, topk_ids,
+                            static_cast<const int*>(counts), static_cast<uint8_t*>(gathered), xs_t,
+                            topk_pos, cu_tokens, tiles, cu_tiles, num_tokens, num_topk, hidden,
+                            num_expert_local, expert_base, scale_tile, m_pad));
   return HPC_OK;
 }
 
@@ -221,10 +229,10 @@ static int reduce(void* y, const void* x, const int* topk_pos, const float* topk
   const long long work = static_cast<long long>(num_tokens) * (hidden / 8);
   if (work == 0) return HPC_OK;
   const int grid = static_cast<int>((work + 255) / 256);
-  moe_reduce_kernel<<<grid, 256, 0, stream>>>(
-      static_cast<__nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(x), topk_pos, topk_scale,
-      static_cast<const __nv_bfloat16*>(shared), num_tokens, hidden, num_topk);
-  HPC_CUDA_CHECK(cudaGetLastError());
+  HPC_CUDA_CHECK(launch_pdl(moe_reduce_kernel, dim3(grid), dim3(256), 0, stream, 1,
+                            static_cast<__nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(x),
+                            topk_pos, topk_scale, static_cast<const __nv_bfloat16*>(shared),
+                            num_tokens, hidden, num_topk));
   return HPC_OK;
 }
 

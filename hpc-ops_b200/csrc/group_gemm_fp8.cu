@@ -44,6 +44,8 @@ constexpr int kThreads = 384;
 constexpr int kMaxGroups = 512;
 constexpr int kEpiBar = 2;
 constexpr int kTileQ = 4;
+constexpr int kXsSlots = kStages + 2;  // activation-scale ring (see the producer)
+constexpr int kMaxKB = 128;            // K blocks per tile whose weight scales are staged (K <= 16384)
 
 struct Params {
   const int* seqlens;      // [G] rows per group
@@ -62,8 +64,9 @@ struct Params {
   int kpad4;
   int scale_tile;  // column padding granule of the transposed activation-scale layout
   int use_bf16_mul;
-  int* tile_counter;  // dynamic tile scheduler (zeroed by the launcher)
+  int* tile_counter;  // dynamic tile scheduler: [0] next tile, [1] CTAs done (self-resetting)
   int debug;  // HPC_B200_MOE_DEBUG diagnostics (timing experiments only; results are wrong when set)
+  long long* debug_out;  // debug & 8: per CTA {cycles, K blocks, ns, tiles} of the MMA thread
 };
 
 __device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float2 f) {
@@ -102,18 +105,13 @@ struct Sched {
   int nt_count;
 };
 
-// dynamic shared memory: operand stages, schedule arrays, amax exchange, barriers, tile queue, TMEM
-// slot; the cluster variant appends kTileQ more barriers behind that
-constexpr int kSmemBytesBase = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGroups) * 4 + 256 * 4 +
-                               (2 * kStages + 4 + 2 * kTileQ) * 8 + kTileQ * 4 + 16;
-constexpr int kSmemBytes = kSmemBytesBase + kTileQ * 8;
-static_assert(kSmemBytesBase % 8 == 0, "cluster barriers must be 8-byte aligned");
+// dynamic shared memory: operand stages, schedule arrays, amax exchange, scale rings, barriers,
+// tile queue, TMEM slot
+constexpr int kSmemBytes = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGroups) * 4 + 256 * 4 +
+                           kXsSlots * kBM * 4 + kTileQ * 2 * kMaxKB * 4 +
+                           (2 * kStages + 4 + 2 * kTileQ + kXsSlots) * 8 + kTileQ * 4 + 16;
 
-// kPair: tiles are enumerated in units of two m-tiles (2u, 2u+1) of one (group, n-tile); CTA
-// `rank` of the 2-CTA cluster takes m-tile 2u + rank, which may lie past the group's last m-tile
-// (nvalid == 0: the CTA only relays its half of the weight tile).
-template <bool kPair>
-__device__ __forceinline__ bool decode_tile(const Sched& s, int tile, int rank, TileInfo& t) {
+__device__ __forceinline__ bool decode_tile(const Sched& s, int tile, TileInfo& t) {
   if (tile >= s.cu_tiles[s.num_group]) return false;
   int lo = 0, hi = s.num_group - 1;
   while (lo < hi) {
@@ -128,32 +126,16 @@ __device__ __forceinline__ bool decode_tile(const Sched& s, int tile, int rank, 
   const int local = tile - s.cu_tiles[g];
   const int mtiles = (s.rows[g] + kBM - 1) / kBM;
   t.g = g;
-  if constexpr (kPair) {
-    const int munits = (mtiles + 1) >> 1;
-    t.nt = local / munits;
-    t.mt = 2 * (local - t.nt * munits) + rank;
-    t.row0 = s.row_start[g] + t.mt * kBM;
-    const int left = s.rows[g] - t.mt * kBM;
-    t.nvalid = left <= 0 ? 0 : (left < kBM ? left : kBM);
-    t.scol0 = s.pad_base[g] + t.mt * kBM;
-  } else {
-    t.nt = local / mtiles;
-    t.mt = local - t.nt * mtiles;
-    t.row0 = s.row_start[g] + t.mt * kBM;
-    const int left = s.rows[g] - t.mt * kBM;
-    t.nvalid = left < kBM ? left : kBM;
-    t.scol0 = s.pad_base[g] + t.mt * kBM;
-  }
+  t.nt = local / mtiles;
+  t.mt = local - t.nt * mtiles;
+  t.row0 = s.row_start[g] + t.mt * kBM;
+  const int left = s.rows[g] - t.mt * kBM;
+  t.nvalid = left < kBM ? left : kBM;
+  t.scol0 = s.pad_base[g] + t.mt * kBM;
   return true;
 }
 
-// kCluster (experimental, HPC_B200_MOE_CLUSTER=1): the grid is launched as clusters of two CTAs that
-// work on the two m-tiles of one (group, n-tile) pair in lockstep. Each CTA fetches half of the
-// 256-row weight tile and TMA-multicasts it to both, so the L2 -> SM traffic per CTA and K block
-// drops from 48 KB to 32 KB (the measured bound of this kernel). Stage release (`empty`) needs both
-// CTAs' MMAs (multicast commit); CTA 0 claims the tiles and publishes them to CTA 1's queue through
-// distributed shared memory.
-template <bool kBlockwise, bool kFused, bool kCluster>
+template <bool kBlockwise, bool kFused>
 __global__ void __launch_bounds__(kThreads, 1)
     group_gemm_fp8_kernel(const __grid_constant__ CUtensorMap tmap_a,
                           const __grid_constant__ CUtensorMap tmap_b, const Params p) {
@@ -164,25 +146,51 @@ __global__ void __launch_bounds__(kThreads, 1)
   int* s_rows = s_pad_base + kMaxGroups;
   int* s_row_start = s_rows + kMaxGroups;
   float* s_amax = reinterpret_cast<float*>(s_row_start + kMaxGroups);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_amax + 256);
+  float* s_xs = s_amax + 256;                        // [kXsSlots][128] activation scales of a K block
+  float* s_ws = s_xs + kXsSlots * kBM;               // [kTileQ][2][kMaxKB] weight scales of a tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ws + kTileQ * 2 * kMaxKB);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* part_full = bars + 2 * kStages;
   uint64_t* part_empty = part_full + 2;
   uint64_t* tq_full = part_empty + 2;   // tile-id queue (kTileQ slots): producer -> consumers
   uint64_t* tq_empty = tq_full + kTileQ;
-  int* s_tileq = reinterpret_cast<int*>(tq_empty + kTileQ);
+  uint64_t* xs_full = tq_empty + kTileQ;  // [kXsSlots]
+  int* s_tileq = reinterpret_cast<int*>(xs_full + kXsSlots);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_tileq + kTileQ);
-  // cluster mode only: CTA 0's view of "CTA 1 has consumed queue slot i" (lives behind everything
-  // else so that the non-cluster layout is unchanged)
-  uint64_t* tq_peer = reinterpret_cast<uint64_t*>(smem + kSmemBytesBase);
-  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int KB = (p.k + kBK - 1) / kBK;  // a ragged last K block is zero-filled by TMA
   const int nt_count = kFused ? (p.n / 2 + 127) / 128 : (p.n + kBN - 1) / kBN;
+  const int nblk_per_group = p.n / 128;
+
+  // ---- set-up that touches no global memory (overlaps the previous kernel under PDL) ----
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int i = 0; i < kStages; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&part_full[i], 1);
+      mbar_init(&part_empty[i], 8);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < kTileQ; i++) {
+      mbar_init(&tq_full[i], 1);
+      mbar_init(&tq_empty[i], 9);  // MMA thread + 8 epilogue warps
+    }
+    for (int i = 0; i < kXsSlots; i++) mbar_init(&xs_full[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  pdl_launch_dependents();
+  pdl_wait();  // routing (seqlens, gathered rows, scales) / the previous GEMM's output are complete
 
   // ---- schedule prologue: every CTA derives the same tile list from seqlens ----
   if (warp == 2) {
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int r = g < p.num_group ? p.seqlens[g] : 0;
       const int mt = (r + kBM - 1) / kBM;
       const int pd = (r + p.scale_tile - 1) / p.scale_tile * p.scale_tile;
-      int it = (kCluster ? (mt + 1) / 2 : mt) * nt_count, ip = pd;
+      int it = mt * nt_count, ip = pd;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int a = __shfl_up_sync(0xffffffffu, it, o);
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       if (g < p.num_group) {
-        s_cu_tiles[g] = carry_tiles + it - (kCluster ? (mt + 1) / 2 : mt) * nt_count;
+        s_cu_tiles[g] = carry_tiles + it - mt * nt_count;
         s_pad_base[g] = carry_pad + ip - pd;
         s_rows[g] = r;
         s_row_start[g] = p.cu_seqlens[g];
@@ -214,57 +222,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     if (lane == 0) s_cu_tiles[p.num_group] = carry_tiles;
   }
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int i = 0; i < kStages; i++) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kCluster ? 2 : 1);  // cluster: released by both CTAs' MMAs
-    }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&part_full[i], 1);
-      mbar_init(&part_empty[i], 8);  // one arrive per epilogue warp
-    }
-    for (int i = 0; i < kTileQ; i++) {
-      mbar_init(&tq_full[i], 1);
-      mbar_init(&tq_empty[i], 9);  // MMA thread + 8 epilogue warps
-      if constexpr (kCluster) mbar_init(&tq_peer[i], 10);  // CTA 1: + its producer thread
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
   tc_fence_before();
-  if constexpr (kCluster) {
-    cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   Sched sched{s_cu_tiles, s_pad_base, s_rows, s_row_start, p.num_group, nt_count};
-  // consumer side of the tile queue: wait for slot `qs`, read it, release it
-  auto queue_wait = [&](uint32_t qs, uint32_t parity) {
-    if constexpr (kCluster) {
-      mbar_wait_cluster(&tq_full[qs], parity);
-    } else {
-      mbar_wait(&tq_full[qs], parity);
-    }
-  };
-  auto queue_release = [&](uint32_t qs) {
-    if constexpr (kCluster) {
-      if (crank == 0) {
-        mbar_arrive(&tq_empty[qs]);
-      } else {
-        mbar_arrive_cluster(map_to_cta(smem_u32(&tq_peer[qs]), 0));
-      }
-    } else {
-      mbar_arrive(&tq_empty[qs]);
-    }
-  };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -280,74 +243,74 @@ __global__ void __launch_bounds__(kThreads, 1)
       // Dynamic scheduler: tiles are claimed from a global counter, so tiles with neighbouring ids
       // (the m-tiles sharing one weight tile) start within a short window on different CTAs and
       // share that weight tile through L2. The id of the next tile is claimed one tile ahead.
-      int next_tile = (!kCluster || crank == 0) ? atomicAdd(p.tile_counter, 1) : 0;
+      int next_tile = atomicAdd(p.tile_counter, 1);
       while (true) {
-        int tile;
-        bool valid;
-        if (!kCluster || crank == 0) {
-          tile = next_tile;
-          valid = decode_tile<kCluster>(sched, tile, 0, t);
-          const uint32_t qs = tq % kTileQ;
-          const uint32_t par = ((tq / kTileQ) & 1) ^ 1;
-          mbar_wait(&tq_empty[qs], par);
-          s_tileq[qs] = valid ? tile : -1;
-          if constexpr (kCluster) {
-            mbar_wait_cluster(&tq_peer[qs], par);  // CTA 1 is done with this slot as well
-            st_dsmem_u32(map_to_cta(smem_u32(&s_tileq[qs]), 1), static_cast<uint32_t>(valid ? tile : -1));
-            mbar_arrive_cluster(map_to_cta(smem_u32(&tq_full[qs]), 1));
-          }
-          mbar_arrive(&tq_full[qs]);
-          tq++;
+        const int tile = next_tile;
+        const bool valid = decode_tile(sched, tile, t);
+        const uint32_t qs = tq % kTileQ;
+        mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1);
+        s_tileq[qs] = valid ? tile : -1;
+        const int nb0 = kFused ? t.nt : t.nt * 2;
+        int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
+        if (nb1 >= nblk_per_group) nb1 = nb0;
+        if (kBlockwise && valid) {
+          // the tile's weight scales (KB floats for each 128-column half) travel with its queue slot
+          const uint32_t bytes = static_cast<uint32_t>(p.kpad4) * 4u;
+          mbar_arrive_expect_tx(&tq_full[qs], 2 * bytes);
+          const float* ws = p.wscale + static_cast<long long>(t.g) * nblk_per_group * p.kpad4;
+          bulk_load_1d(s_ws + (qs * 2 + 0) * kMaxKB, ws + static_cast<long long>(nb0) * p.kpad4, bytes, &tq_full[qs]);
+          bulk_load_1d(s_ws + (qs * 2 + 1) * kMaxKB, ws + static_cast<long long>(nb1) * p.kpad4, bytes, &tq_full[qs]);
         } else {
-          const uint32_t qs = tq % kTileQ;
-          queue_wait(qs, (tq / kTileQ) & 1);
-          tile = s_tileq[qs];
-          queue_release(qs);
-          tq++;
-          valid = tile >= 0;
-          if (valid) decode_tile<kCluster>(sched, tile, 1, t);
+          mbar_arrive(&tq_full[qs]);
         }
+        tq++;
         if (!valid) break;
-        if (!kCluster || crank == 0) next_tile = atomicAdd(p.tile_counter, 1);
+        next_tile = atomicAdd(p.tile_counter, 1);
         const int nrow0 = kFused ? t.nt * 128 : t.nt * kBN;
         const int nrow1 = kFused ? p.n / 2 + t.nt * 128 : t.nt * kBN + 128;
+        // activation scales of the tile's rows: 16-byte granules covering the valid rows
+        const uint32_t xs_bytes = static_cast<uint32_t>((t.nvalid + 3) / 4) * 16u;
         for (int kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % kStages;
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
-          if constexpr (kCluster) {
-            // the stage is free once BOTH CTAs have consumed it: this CTA writes into both. (A plain
-            // wait: nothing written by the consumers is read here; a cluster-scope acquire would
-            // invalidate L1 every K block.)
-            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-            const bool real = t.nvalid > 0;
-            mbar_arrive_expect_tx(&full[s], real ? kStageBytes : kBBytes);
-            if (real) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
-            // this CTA's half of the weight tile goes to both CTAs (same offsets, both `full`s)
-            tma_load_3d_mcast(b_dst + crank * (kBBytes / 2), &tmap_b, &full[s], kb * kBK,
-                              crank == 0 ? nrow0 : nrow1, t.g, static_cast<uint16_t>(3));
-          } else {
-            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-            if (p.debug & 3) {  // diagnostics: leave out the weight (1) / activation (2) tile loads
-              const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes);
-              if (bytes == 0) {
-                mbar_arrive(&full[s]);
-              } else {
-                mbar_arrive_expect_tx(&full[s], bytes);
-              }
-              if (!(p.debug & 2)) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
-              if (!(p.debug & 1)) {
-                tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
-                tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
-              }
-              continue;
-            }
-            mbar_arrive_expect_tx(&full[s], kStageBytes);
-            tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
-            tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
-            tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          if constexpr (kBlockwise) {
+            // Ring of kStages + 2 slots, no "empty" barrier needed: this K block `it` is loaded once
+            // stage s is free, i.e. MMA(it - kStages) has completed, which was issued only after the
+            // epilogue finished with K block it - kStages - 2 -- the previous user of this slot.
+            const uint32_t xsl = it % kXsSlots;
+            mbar_arrive_expect_tx(&xs_full[xsl], xs_bytes);
+            bulk_load_1d(s_xs + xsl * kBM, p.xscale_t + static_cast<long long>(kb) * p.m_pad + t.scol0,
+                         xs_bytes, &xs_full[xsl]);
           }
+          if (p.debug & 3) {  // diagnostics: leave out the weight (1) / activation (2) tile loads
+            const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes);
+            if (bytes == 0) {
+              mbar_arrive(&full[s]);
+            } else {
+              mbar_arrive_expect_tx(&full[s], bytes);
+            }
+            if (!(p.debug & 2)) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+            if (!(p.debug & 1)) {
+              tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
+              tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+          tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
+          tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
         }
+      }
+      // the last CTA out re-arms the scheduler for the next launch (no memset between launches:
+      // a memset node would break a PDL chain, and a graph replay needs nothing else)
+      __threadfence();
+      if (atomicAdd(p.tile_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+        p.tile_counter[0] = 0;
+        p.tile_counter[1] = 0;
+        __threadfence();
       }
     } else if (warp == 1 && lane == 0) {
       // =========================== tcgen05 issuer =========================================
@@ -357,27 +320,21 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t it = 0;   // K-block counter (smem ring)
       uint32_t acc_it = 0;  // accumulator-buffer use counter
       uint32_t tq = 0;
-      TileInfo t;
+      uint32_t ntiles = 0;
+      unsigned long long g0 = 0;
+      long long c0 = 0;
+      if (p.debug & 8) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+        c0 = clock64();
+      }
       while (true) {
         const uint32_t qs = tq % kTileQ;
-        queue_wait(qs, (tq / kTileQ) & 1);
+        mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
         const int tile = s_tileq[qs];
-        queue_release(qs);
+        mbar_arrive(&tq_empty[qs]);
         tq++;
         if (tile < 0) break;
-        decode_tile<kCluster>(sched, tile, static_cast<int>(crank), t);
-        if constexpr (kCluster) {
-          if (t.nvalid == 0) {
-            // relay-only CTA of a pair: nothing to multiply, but both CTAs' stages must keep turning
-            for (int kb = 0; kb < KB; kb++, it++) {
-              const uint32_t s = it % kStages;
-              mbar_wait(&full[s], (it / kStages) & 1);  // the multicast data has landed here too
-              mbar_arrive(&empty[s]);
-              mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&empty[s]), crank ^ 1u));
-            }
-            continue;
-          }
-        }
+        ntiles++;
         for (int kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % kStages;
           const bool new_acc = kBlockwise || kb == 0;
@@ -392,16 +349,25 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int k = 0; k < 4; k++) {
             umma_f8(d, ad + k * 2, bd + k * 2, idesc, (k > 0) || !new_acc);
           }
-          if constexpr (kCluster) {
-            umma_commit_mcast(&empty[s], static_cast<uint16_t>(3));  // frees the stage in both CTAs
-          } else {
-            umma_commit(&empty[s]);
-          }
+          // The accumulator hand-over is the critical path (MMA -> drain -> next MMA into this
+          // buffer); the stage release is not (the producer runs kStages ahead). Commits are
+          // processed in order, so "accumulator ready" goes first (measured with
+          // tools/umma_rate.py: 725 -> 563 cycles per K block).
           if (kBlockwise || kb == KB - 1) {
             umma_commit(&part_full[buf]);
             acc_it++;
           }
+          umma_commit(&empty[s]);
         }
+      }
+      if (p.debug & 8) {
+        unsigned long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        long long* o = p.debug_out + (kFused ? 0 : 4 * 256) + 4 * blockIdx.x;
+        o[0] = clock64() - c0;
+        o[1] = it;
+        o[2] = static_cast<long long>(g1 - g0);
+        o[3] = ntiles;
       }
     }
   } else {
@@ -411,27 +377,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int quad = warp & 3;
     const int row_local = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int nblk_per_group = p.n / 128;
 
     uint32_t acc_it = 0;
     uint32_t tq = 0;
     TileInfo t;
     while (true) {
       const uint32_t qs = tq % kTileQ;
-      queue_wait(qs, (tq / kTileQ) & 1);
+      mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
       const int tile = s_tileq[qs];
-      __syncwarp();
-      if (lane == 0) queue_release(qs);
       tq++;
-      if (tile < 0) break;
-      decode_tile<kCluster>(sched, tile, static_cast<int>(crank), t);
-      if constexpr (kCluster) {
-        if (t.nvalid == 0) continue;  // relay-only CTA: the MMA thread produces no accumulator
+      if (tile < 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tq_empty[qs]);
+        break;
       }
+      decode_tile(sched, tile, t);
       const bool row_valid = row_local < t.nvalid;
-      const int nb0 = kFused ? t.nt : t.nt * 2;
-      const int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
-      const bool nb1_valid = nb1 < nblk_per_group;
 
       float2 acc[2][32];  // [half][pair]: 64 columns of each 128-column half
 #pragma unroll
@@ -440,26 +401,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int i = 0; i < 32; i++) acc[h][i] = make_float2(0.f, 0.f);
 
       if constexpr (kBlockwise) {
-        const float* xs_ptr = p.xscale_t + t.scol0 + row_local;
-        const float* ws0_ptr = p.wscale + (static_cast<long long>(t.g) * nblk_per_group + nb0) * p.kpad4;
-        const float* ws1_ptr =
-            p.wscale + (static_cast<long long>(t.g) * nblk_per_group + (nb1_valid ? nb1 : nb0)) * p.kpad4;
-        // block scales are prefetched two K blocks ahead (L2 latency ~ one MMA block)
-        float xs_q[2], w0_q[2], w1_q[2];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const bool ok = j < KB;
-          xs_q[j] = (ok && row_valid) ? __ldg(xs_ptr + static_cast<long long>(j) * p.m_pad) : 0.f;
-          w0_q[j] = ok ? __ldg(ws0_ptr + j) : 0.f;
-          w1_q[j] = ok ? __ldg(ws1_ptr + j) : 0.f;
-        }
+        const float* ws0 = s_ws + (qs * 2 + 0) * kMaxKB;
+        const float* ws1 = s_ws + (qs * 2 + 1) * kMaxKB;
         for (int kb = 0; kb < KB; kb++, acc_it++) {
-          const float xs = xs_q[kb & 1], w0 = w0_q[kb & 1], w1 = w1_q[kb & 1];
-          if (kb + 2 < KB) {
-            xs_q[kb & 1] = row_valid ? __ldg(xs_ptr + static_cast<long long>(kb + 2) * p.m_pad) : 0.f;
-            w0_q[kb & 1] = __ldg(ws0_ptr + kb + 2);
-            w1_q[kb & 1] = __ldg(ws1_ptr + kb + 2);
-          }
+          // block scales from shared memory (staged by the producer with the operands): no global
+          // load latency in this loop
+          const uint32_t xsl = acc_it % kXsSlots;
+          mbar_wait(&xs_full[xsl], (acc_it / kXsSlots) & 1);
+          const float xs = row_valid ? s_xs[xsl * kBM + row_local] : 0.f;
+          const float w0 = ws0[kb], w1 = ws1[kb];
           const uint32_t buf = acc_it & 1;
           mbar_wait(&part_full[buf], (acc_it >> 1) & 1);
           tc_fence_after();
@@ -522,6 +472,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) mbar_arrive(&part_empty[buf]);
         acc_it++;
       }
+      // the queue slot (tile id + its weight scales) is free once the K loop is through
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tq_empty[qs]);
 
       // ---------------- tile epilogue ----------------
       const long long grow = static_cast<long long>(t.row0) + row_local;
@@ -601,28 +554,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 
   tc_fence_before();
-  if constexpr (kCluster) {
-    cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it is done too
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// HPC_B200_MOE_CLUSTER=1 selects the experimental 2-CTA weight-multicast variant (off by default:
-// not yet validated on hardware).
-static bool use_cluster_variant() {
-  static const bool on = [] {
-    const char* e = std::getenv("HPC_B200_MOE_CLUSTER");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
+static long long* g_dbg_buf[64] = {nullptr};  // HPC_B200_MOE_DEBUG & 8: [2][256][4] int64 per device
 
-template <bool kBlockwise, bool kFused, bool kCluster>
-static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
-                       cudaStream_t stream) {
-  auto kern = group_gemm_fp8_kernel<kBlockwise, kFused, kCluster>;
+template <bool kBlockwise, bool kFused>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+  auto kern = group_gemm_fp8_kernel<kBlockwise, kFused>;
   static bool configured[64] = {false};
   const int dev = device_slot();
   if (!configured[dev]) {
@@ -635,33 +575,18 @@ static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Param
     return e ? std::atoi(e) : 0;
   }();
   pp.debug = dbg;
-  pp.tile_counter = launch_counter(stream);  // dynamic tile scheduler
-  if (pp.tile_counter == nullptr) return HPC_ERR_CUDA;
-  if constexpr (kCluster) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((sm_count() / 2) * 2, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    HPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, pp));
-  } else {
-    kern<<<sm_count(), kThreads, kSmemBytes, stream>>>(ta, tb, pp);
-    HPC_CUDA_CHECK(cudaGetLastError());
+  pp.debug_out = nullptr;
+  if (dbg & 8) {
+    if (g_dbg_buf[dev] == nullptr) {
+      HPC_CUDA_CHECK(cudaMalloc(&g_dbg_buf[dev], 2 * 4 * 256 * sizeof(long long)));
+      HPC_CUDA_CHECK(cudaMemset(g_dbg_buf[dev], 0, 2 * 4 * 256 * sizeof(long long)));
+    }
+    pp.debug_out = g_dbg_buf[dev];
   }
+  pp.tile_counter = scheduler_counter(stream);  // self-resetting pair of ints, one per stream
+  if (pp.tile_counter == nullptr) return HPC_ERR_CUDA;
+  HPC_CUDA_CHECK(launch_pdl(kern, dim3(sm_count()), dim3(kThreads), kSmemBytes, stream, 1, ta, tb, pp));
   return HPC_OK;
-}
-
-template <bool kBlockwise, bool kFused>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
-  if (use_cluster_variant()) return launch_impl<kBlockwise, kFused, true>(ta, tb, p, stream);
-  return launch_impl<kBlockwise, kFused, false>(ta, tb, p, stream);
 }
 
 // Common launcher. mode bits: 1 = blockwise scales, 2 = fused activation epilogue.
@@ -675,6 +600,14 @@ int run(int mode, const void* x, const void* w, const int* seqlens, const int* c
     HPC_REQUIRE(k % 128 == 0 && k >= 128, "group gemm: k (%d) must be a multiple of 128", k);
     HPC_REQUIRE(n % 128 == 0, "group gemm: n (%d) must be a multiple of 128", n);
     if (mode & 2) HPC_REQUIRE(n % 256 == 0, "fused act: gate_up rows (%d) must be a multiple of 256", n);
+    HPC_REQUIRE(kpad4 % 4 == 0 && kpad4 * 128 >= k && kpad4 <= kMaxKB,
+                "group gemm: weight-scale row length %d must be a multiple of 4 covering k/128 (<= %d)",
+                kpad4, kMaxKB);
+    HPC_REQUIRE(m_pad % 4 == 0 && scale_tile % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(xscale_t) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(wscale) & 15) == 0,
+                "group gemm: activation-scale columns (%d, tile %d) must be multiples of 4 and the "
+                "scale tensors 16-byte aligned", m_pad, scale_tile);
   } else {
     HPC_REQUIRE(k % 16 == 0 && k >= 16, "group gemm: k (%d) must be a multiple of 16", k);
     HPC_REQUIRE(n % 64 == 0, "group gemm: n (%d) must be a multiple of 64", n);
@@ -746,6 +679,16 @@ int scale_tile_from_avg(int avg) {
 }  // namespace b200
 
 using namespace b200;  // NOLINT
+
+// diagnostics (HPC_B200_MOE_DEBUG=8): copy the MMA threads' per-CTA counters of the last Gate-Up
+// (fused) and Down / plain launches to the host: out[2][256][4] = {cycles, K blocks, ns, tiles}
+extern "C" int hpc_group_gemm_debug_counters(long long* out_host) {
+  const int dev = device_slot();
+  HPC_REQUIRE(ggemm::g_dbg_buf[dev] != nullptr, "no debug counters recorded (HPC_B200_MOE_DEBUG=8?)");
+  HPC_CUDA_CHECK(cudaMemcpy(out_host, ggemm::g_dbg_buf[dev], 2 * 4 * 256 * sizeof(long long),
+                            cudaMemcpyDeviceToHost));
+  return HPC_OK;
+}
 
 // replaces reference src/group_gemm/group_gemm.h:22-29 (group_gemm_blockwise_fp8_async). The
 // tmas / tiles / cu_tiles / task_map / num_waves / update_tma / use_pdl arguments are accepted for

@@ -67,6 +67,36 @@ int* launch_counter(cudaStream_t stream) {
   return slot;
 }
 
+int* scheduler_counter(cudaStream_t stream) {
+  constexpr int kSlots = 128;
+  struct Entry {
+    cudaStream_t stream;
+    bool used;
+  };
+  static int* pool[64] = {nullptr};
+  static Entry table[64][kSlots] = {};
+  static std::mutex mu;
+  const int dev = device_slot();
+  std::lock_guard<std::mutex> lock(mu);
+  if (pool[dev] == nullptr) {
+    if (cudaMalloc(&pool[dev], kSlots * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(pool[dev], 0, kSlots * 2 * sizeof(int)) != cudaSuccess) {
+      set_last_error("scheduler_counter: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      pool[dev] = nullptr;
+      return nullptr;
+    }
+  }
+  int free_slot = -1;
+  for (int i = 0; i < kSlots; i++) {
+    if (table[dev][i].used && table[dev][i].stream == stream) return pool[dev] + 2 * i;
+    if (!table[dev][i].used && free_slot < 0) free_slot = i;
+  }
+  if (free_slot < 0) free_slot = static_cast<int>((reinterpret_cast<uintptr_t>(stream) >> 4) % kSlots);
+  table[dev][free_slot].stream = stream;
+  table[dev][free_slot].used = true;
+  return pool[dev] + 2 * free_slot;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -42,6 +42,12 @@ int device_slot();
 // rotating per-device pool of 256 and cleared with cudaMemsetAsync on `stream`. The pool is
 // allocated on the first call per device, which therefore must not happen inside a stream capture.
 int* launch_counter(cudaStream_t stream);
+// Two zeroed int32 (work counter, finished-CTA counter) owned by `stream` for kernels that re-arm
+// their scheduler themselves (the last CTA resets both): no memset between launches, so PDL chains
+// and graph replays are unaffected. One slot per (device, stream), allocated and zeroed on first
+// use (not inside a stream capture); launches on one stream are serialised, so the slot is never
+// shared by two running kernels.
+int* scheduler_counter(cudaStream_t stream);
 
 // Encode a tiled TMA descriptor (uint8 elements). dims/strides innermost-first; strides in bytes for
 // dims 1..rank-1. Returns 0 on success.

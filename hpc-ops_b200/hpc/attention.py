@@ -1,7 +1,8 @@
 """Attention operators of the hot path (API of reference hpc/attention.py).
 
 Implemented in this build (sm_100a):
-  * attention_decode_fp8            — quant_type QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR
+  * attention_decode_fp8            — quant_type QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR and
+                                      QPERTOKEN_PERHEAD_KPERTOKEN_PERHEAD_VPERHEAD (in-cache k scales)
   * get_attention_decode_task_workspace / assign_attention_decode_task (CPU and CUDA)
   * print_attention_decode_task
 The host side does what the reference's torch entry does (validation, scratch allocation, stride
@@ -93,6 +94,18 @@ def _decode_fp8_prepare(
     _require(q.stride(2) == 1 and q.stride(1) == num_dim_qk, "q must be contiguous in (head, dim)")
     _require(kcache.stride(3) == 1 and vcache.stride(3) == 1, "kv cache innermost dim must be contiguous")
     _require(qscale.dtype == torch.float32 and vscale.dtype == torch.float32, "scales must be float32")
+    _require(int(quant_type) in (0, 1), "attention_decode_fp8 supports quant_type 0 and 1")
+    if int(quant_type) == 0:
+        # per-token k scales: fp32 words in the cache allocation's extra rows, logical shape
+        # [blocks, bs/32, Hkv, D/4] f32, passed as an fp8 view or as f32; they share the cache's
+        # strides (reference src/attention/entry.cc:245-253, tests/..qkpertoken..fp8.py:340-385)
+        ks_unit = 4 // kscale.element_size()  # strides in elements -> floats
+        _require(kscale.element_size() in (1, 4) and kscale.dim() == 4, "kscale must be [blocks, bs/32, Hkv, D/4] f32 (or its fp8 view)")
+        for i in range(3):
+            _require(kscale.stride(i) * kscale.element_size() == kcache.stride(i),
+                     "k scale rows must be the extra rows of the kcache allocation (same strides)")
+        _require(kscale.stride(3) == 1 and kscale.data_ptr() % 4 == 0 and ks_unit >= 1, "bad kscale layout")
+        _require(vscale.numel() == num_head_k, "vscale must hold one scale per kv head")
 
     if output is not None:
         y = output
@@ -309,7 +322,10 @@ def attention_decode_fp8(
       kcache     [num_blocks, 64, num_head_kv, 128] float8_e4m3fn, any strides on dims 0-2
       vcache     same; unused slots of a request's last block must be zero
       block_ids  [num_batch, max_blocks] int32;  num_seq_kvcache [num_batch] int32
-      qscale     [num_batch * num_seq_q, num_head_q] f32;  kscale, vscale [1] f32
+      qscale     [num_batch * num_seq_q, num_head_q] f32
+      kscale, vscale  quant_type 1: [1] f32 each; quant_type 0: kscale = the cache allocation's
+                 scale rows (f32 [num_blocks, 2, num_head_kv, 32], same strides as kcache),
+                 vscale [num_head_kv] f32
       task_map   from get_attention_decode_task_workspace + assign_attention_decode_task
     Returns bf16 [num_batch * num_seq_q, num_head_q, 128].
     """

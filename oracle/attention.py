@@ -93,5 +93,50 @@ def decode_fp8_kvpertensor(q, kcache, vcache, block_ids, kv_lens_total, q_scale,
     return out.reshape(-1, num_head_q, head_dim)
 
 
-# synthetic input builder: lives in synth/ (neutral code), re-exported for the tests
-from synth.decode import make_decode_fp8_inputs  # noqa: E402,F401
+def decode_fp8_kpertoken(q, kcache, vcache, block_ids, kv_lens_total, q_scale, k_scale, v_scale,
+                         num_seq_q, per_token_qscale=True):
+    """FP8 paged decode attention, q and k per-token/per-head scales, v per-head scale.
+
+    Follows reference tests/test_attention_decode_qkpertoken_perhead_vperhead_fp8.py:55-132:
+      S = Q K^T / sqrt(D) * k_scale[token, head] * q_scale; causal mask; P = exp(S - max); sum over
+      unquantised P; P*256 -> e4m3; Y = (P V) / sum * v_scale[head] / 256; bf16.
+      k_scale: the cache's scale rows, fp8 view or f32, [blocks, bs/32, Hkv, D or D/4];
+      v_scale [Hkv] f32. q_scale indexing as in decode_fp8_kvpertensor.
+    """
+    num_batch = kv_lens_total.shape[0]
+    num_head_q, head_dim = q.shape[1], q.shape[2]
+    num_head_kv, block_size = kcache.shape[2], kcache.shape[1]
+    g = num_head_q // num_head_kv
+    qv = q.reshape(num_batch, num_seq_q, num_head_q, head_dim)
+    qs = q_scale.reshape(-1, num_head_q)
+    ks = k_scale.contiguous()
+    if ks.element_size() == 1:
+        ks = ks.view(torch.float32)
+    out = torch.empty(qv.shape, dtype=torch.bfloat16, device=q.device)
+    for bi in range(num_batch):
+        seqlen = int(kv_lens_total[bi])
+        nblk = (seqlen + block_size - 1) // block_size
+        ids = block_ids[bi, :nblk]
+        qb = qv[bi].transpose(0, 1).float()
+        kb = _gather_kv(kcache, ids, seqlen, num_head_kv, head_dim, g)
+        vb = _gather_kv(vcache, ids, seqlen, num_head_kv, head_dim, g)
+        ksb = (ks[ids.long()].permute(0, 1, 3, 2).reshape(-1, num_head_kv).transpose(0, 1)[:, :seqlen]
+               .repeat_interleave(g, dim=0)).float()
+        p = qb @ kb.transpose(-1, -2)
+        if per_token_qscale:
+            sc = qs[bi * num_seq_q:(bi + 1) * num_seq_q].transpose(0, 1)[:, :, None]
+        else:
+            sc = qs[bi][:, None, None]
+        p = p / math.sqrt(head_dim) * ksb.unsqueeze(1) * sc
+        p = p.masked_fill(~_causal_mask(num_seq_q, seqlen, q.device), float("-inf"))
+        w = torch.exp(p - p.max(dim=-1)[0][:, :, None])
+        gsum = w.sum(dim=-1)[:, :, None]
+        w = (w * 256.0).to(torch.float8_e4m3fn).float()
+        y = torch.matmul(w, vb) / gsum
+        y = y * v_scale[:, None, None].repeat_interleave(g, dim=0) / 256.0
+        out[bi] = y.transpose(0, 1).to(torch.bfloat16)
+    return out.reshape(-1, num_head_q, head_dim)
+
+
+# synthetic input builders: live in synth/ (neutral code), re-exported for the tests
+from synth.decode import make_decode_fp8_inputs, make_decode_fp8_kpt_inputs  # noqa: E402,F401

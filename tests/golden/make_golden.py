@@ -62,6 +62,26 @@ def decode_fp8_case(tag, num_batch, kv_lens, hkv, hq, seed, layout):
     print("wrote", tag, gt.shape)
 
 
+def decode_fp8_kpt_case(tag, num_batch, kv_lens, hkv, hq, seed, layout):
+    """k-per-token variant: the reference's own ref function on the in-cache scale layout."""
+    fn = extract(REF / "tests/test_attention_decode_qkpertoken_perhead_vperhead_fp8.py",
+                 "ref_attn_with_paged_kvcache_func")
+    d = oa.make_decode_fp8_kpt_inputs(num_batch, 1, kv_lens, hkv, hq, seed=seed, layout=layout)
+    lens = d["kv_lens_total"]
+    nblocks = (lens + 63) // 64
+    seqlenq = torch.ones(num_batch, dtype=torch.int32)
+    kdummy = torch.empty(num_batch, hkv, 128)
+    gt = fn(d["q"], kdummy, kdummy, d["kvcache"][:, :, :64], d["block_ids"], nblocks, seqlenq, None,
+            lens - 1, d["q_scale"], d["k_scale"].contiguous(), d["v_scale"])
+    np.savez_compressed(
+        OUT / f"decode_fp8_kpt_{tag}.npz", q=u8(d["q"]), q_scale=d["q_scale"].numpy(),
+        kvcache=u8(d["kvcache"].contiguous()), v_scale=d["v_scale"].numpy(),
+        block_ids=d["block_ids"].numpy(), kv_lens_total=lens.numpy(), out=gt.float().numpy(),
+        meta=np.array([num_batch, 1, hkv, hq, 128, 64]),
+        layout=np.array([0 if layout == "NHD" else 1]))
+    print("wrote kpt", tag, gt.shape)
+
+
 def decode_bf16_c1():
     """BASELINE config 0: test_attention_decode_bf16 bs=2 h=4 d=64 seq=128 on the torch CPU path."""
     fn = extract(REF / "tests/test_attention_decode_bf16.py", "ref_attn_with_paged_kvcache_func")
@@ -261,5 +281,7 @@ if __name__ == "__main__":
     moe_pertensor_case("a", 32, 4, 256, 128, 8, 1, 0, 5)
     decode_fp8_case("b2_nhd", 2, [100, 129], 1, 8, 41, "NHD")
     decode_fp8_case("b5_hnd", 5, [1, 64, 65, 300, 515], 2, 16, 10086, "HND")
+    decode_fp8_kpt_case("b3_nhd", 3, [70, 129, 200], 1, 8, 41, "NHD")
+    decode_fp8_kpt_case("b4_hnd", 4, [1, 64, 65, 300], 2, 8, 10086, "HND")
     decode_bf16_c1()
     taskmap_cases()

@@ -30,8 +30,9 @@ def test_c3_fuse_moe_blockwise_sampled(hpc):
     st = r["parity"]
     print(st)
     assert st["finite"] and st["checked"] == 3 * 4096
-    # rtol = atol = 0.01 as the reference; <= 5 ppm-style allowance for e4m3 re-quantisation ties
-    assert st["outside_tol"] <= 2 and st["rel_l2"] < 0.01, st
+    # criterion documented in bench_extras.moe_c3_parity_ok: reference rtol = atol = 0.01 for
+    # >= 99.5 % of the elements, relative L2 < 2e-3, max |err| < 1 % of the largest output
+    assert bx.moe_c3_parity_ok(st), st
 
 
 def test_c3_down_gemm_k14336_one_expert(hpc):

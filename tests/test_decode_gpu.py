@@ -154,13 +154,13 @@ def _run_decode(hpc, d, num_batch, num_seq_q, hkv, min_process_len=1024, use_tas
         task_map=task_map)
 
 
-def _check(my, gt, tag=""):
+def _check(my, gt, tag="", atol=0.2):
     my = my.float().cpu()
     gt = gt.float().cpu()
     err = (my - gt).abs()
     rel = err.norm() / gt.norm().clamp_min(1e-6)
     assert torch.isfinite(my).all(), f"{tag}: non-finite output"
-    assert torch.allclose(my, gt, atol=0.2), f"{tag}: max abs err {err.max():.4f}"
+    assert torch.allclose(my, gt, atol=atol), f"{tag}: max abs err {err.max():.4f}"
     assert rel < 0.03, f"{tag}: relative error {rel:.4f}"
 
 
@@ -270,12 +270,85 @@ def test_decode_fp8_full_size_c2_sampled(hpc):
         _check(my[bi:bi + 1], gt, f"C2 request {bi}")
 
 
+# ------------------------------------------------------------------------------------------------
+# k-per-token / v-per-head variant (quant_type 0): scales in the cache allocation's extra rows
+# ------------------------------------------------------------------------------------------------
+def _run_decode_kpt(hpc, d, num_batch, num_seq_q, hkv, min_process_len=2048, use_task_map=True):
+    tm = None
+    if use_task_map:
+        tm = hpc.get_attention_decode_task_workspace(num_batch, int(d["kv_lens_total"].max()), hkv,
+                                                     min_process_len)
+        hpc.assign_attention_decode_task(d["kv_lens_total"], tm, hkv, num_seq_q, True, min_process_len)
+    return hpc.attention_decode_fp8(
+        d["q"], d["kcache"], d["vcache"], d["block_ids"], d["kv_lens_total"], d["q_scale"],
+        d["k_scale"], d["v_scale"], mtp=num_seq_q - 1, new_kv_included=True,
+        quant_type=hpc.QuantType.QPERTOKEN_PERHEAD_KPERTOKEN_PERHEAD_VPERHEAD, task_map=tm)
+
+
+def _oracle_kpt(d, num_seq_q):
+    c = {k: v.cpu() for k, v in d.items()}
+    return oa.decode_fp8_kpertoken(c["q"], c["kcache"], c["vcache"], c["block_ids"],
+                                   c["kv_lens_total"], c["q_scale"], c["k_scale"], c["v_scale"],
+                                   num_seq_q)
+
+
+@pytest.mark.parametrize("num_batch", [1, 16, 200])
+@pytest.mark.parametrize("num_seq_q", [1, 2, 3, 4])
+@pytest.mark.parametrize("max_seq_kv", [1024, 4096])
+@pytest.mark.parametrize("kv_head_q_head", [(1, 8), (4, 32)])
+@pytest.mark.parametrize("layout", ["NHD", "HND"])
+@pytest.mark.parametrize("use_dynamic_sched", [False, True])
+def test_decode_fp8_kpertoken_vs_oracle(hpc, num_batch, num_seq_q, max_seq_kv, kv_head_q_head, layout,
+                                        use_dynamic_sched):
+    """Grid of reference tests/test_attention_decode_qkpertoken_perhead_vperhead_fp8.py:446-456
+    (use_dynamic_sched=False = no caller task map), tolerance atol=0.1 (:443)."""
+    hkv, hq = kv_head_q_head
+    if num_batch == 200 and (max_seq_kv == 4096 or not use_dynamic_sched) and hkv == 4:
+        pytest.skip("CPU oracle too slow for this cell; same kernel path as the smaller cells")
+    g = torch.Generator().manual_seed(41)
+    lens = torch.randint(1, max_seq_kv, (num_batch,), generator=g, dtype=torch.int32) + num_seq_q
+    d = oa.make_decode_fp8_kpt_inputs(num_batch, num_seq_q, lens, hkv, hq, seed=41, layout=layout,
+                                      device="cuda")
+    my = _run_decode_kpt(hpc, d, num_batch, num_seq_q, hkv, use_task_map=use_dynamic_sched)
+    _check(my, _oracle_kpt(d, num_seq_q), f"kpt B{num_batch} Sq{num_seq_q} S{max_seq_kv} {kv_head_q_head} {layout}",
+           atol=0.1)
+
+
+@pytest.mark.parametrize("lens", [[1], [2, 64, 65, 127, 128, 129, 255, 256, 257], [40000], [131] * 37])
+@pytest.mark.parametrize("num_seq_q", [1, 4])
+def test_decode_fp8_kpertoken_edge_lengths(hpc, lens, num_seq_q):
+    lens = [max(L, num_seq_q) for L in lens]
+    B = len(lens)
+    d = oa.make_decode_fp8_kpt_inputs(B, num_seq_q, lens, 2, 8, seed=7, device="cuda")
+    for mpl in (64, 1024):
+        my = _run_decode_kpt(hpc, d, B, num_seq_q, 2, min_process_len=mpl)
+        _check(my, _oracle_kpt(d, num_seq_q), f"kpt lens {lens[:4]} Sq{num_seq_q} mpl{mpl}", atol=0.1)
+
+
+def test_decode_fp8_kpertoken_golden_fixtures(hpc):
+    from test_oracle_attention import load_kpt
+
+    for name in ("decode_fp8_kpt_b3_nhd.npz", "decode_fp8_kpt_b4_hnd.npz"):
+        z, d, (B, sq, hkv, hq, D, bs), layout = load_kpt(name)
+        kv = d["kvcache"].cuda()
+        if layout == 1:
+            kv = kv.permute(0, 1, 3, 2, 4).contiguous().permute(0, 1, 3, 2, 4)
+        dd = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+        dd.update(kvcache=kv, kcache=kv[:, 0, :bs], vcache=kv[:, 1, :bs], k_scale=kv[:, 0, bs:])
+        my = _run_decode_kpt(hpc, dd, B, sq, hkv)
+        _check(my, torch.from_numpy(z["out"]), name, atol=0.1)
+
+
 def test_decode_rejects_unsupported(hpc):
     d = oa.make_decode_fp8_inputs(2, 1, [100, 100], 2, 8, seed=1, device="cuda")
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):  # k scales that are not the cache's own rows
         hpc.attention_decode_fp8(d["q"], d["kvcache"][:, 0], d["kvcache"][:, 1], d["block_ids"],
                                  d["kv_lens_total"], d["q_scale"], d["k_scale"], d["v_scale"],
                                  quant_type=hpc.QuantType.QPERTOKEN_PERHEAD_KPERTOKEN_PERHEAD_VPERHEAD)
+    with pytest.raises(RuntimeError):
+        hpc.attention_decode_fp8(d["q"], d["kvcache"][:, 0], d["kvcache"][:, 1], d["block_ids"],
+                                 d["kv_lens_total"], d["q_scale"], d["k_scale"], d["v_scale"],
+                                 quant_type=hpc.QuantType.QPERTENSOR_KPERTENSOR_VPERTENSOR)
     with pytest.raises(RuntimeError):
         hpc.attention_decode_fp8(d["q"].float(), d["kvcache"][:, 0], d["kvcache"][:, 1],
                                  d["block_ids"], d["kv_lens_total"], d["q_scale"], d["k_scale"],

@@ -29,6 +29,27 @@ def test_decode_fp8_oracle_matches_reference_function():
         assert torch.equal(out.float(), ref), (name, (out.float() - ref).abs().max())
 
 
+def load_kpt(name):
+    """golden of the k-per-token decode variant -> (z, dict of tensors as the API takes them)."""
+    z = np.load(G / name)
+    B, sq, hkv, hq, D, bs = map(int, z["meta"])
+    kv = torch.from_numpy(z["kvcache"]).view(torch.float8_e4m3fn)  # [blocks, 2, bs + 2, Hkv, D]
+    d = dict(q=torch.from_numpy(z["q"]).view(torch.float8_e4m3fn), kvcache=kv,
+             kcache=kv[:, 0, :bs], vcache=kv[:, 1, :bs], k_scale=kv[:, 0, bs:],
+             block_ids=torch.from_numpy(z["block_ids"]), kv_lens_total=torch.from_numpy(z["kv_lens_total"]),
+             q_scale=torch.from_numpy(z["q_scale"]), v_scale=torch.from_numpy(z["v_scale"]))
+    return z, d, (B, sq, hkv, hq, D, bs), int(z["layout"][0])
+
+
+def test_decode_fp8_kpertoken_oracle_matches_reference_function():
+    for name in ("decode_fp8_kpt_b3_nhd.npz", "decode_fp8_kpt_b4_hnd.npz"):
+        z, d, (B, sq, hkv, hq, D, bs), _ = load_kpt(name)
+        out = oa.decode_fp8_kpertoken(d["q"], d["kcache"], d["vcache"], d["block_ids"],
+                                      d["kv_lens_total"], d["q_scale"], d["k_scale"], d["v_scale"], sq)
+        ref = torch.from_numpy(z["out"])
+        assert torch.equal(out.float(), ref), (name, (out.float() - ref).abs().max())
+
+
 def test_decode_bf16_config_c1_cpu_plumbing():
     """BASELINE config 0: bs=2 h=4 d=64 seq<=128 bf16 decode through the torch CPU reference path."""
     z = np.load(G / "decode_bf16_c1.npz")

@@ -65,9 +65,24 @@ def main():
     ms = e0.elapsed_time(e1) / a.iters
     flops = 2 * T * K * (2 * I * H + H * I)
     wbytes = E * (2 * I * H + H * I)
-    print(json.dumps({"ms": ms, "tok_per_s": T / ms * 1e3, "tflops": flops / ms / 1e9,
-                      "frac_fp8_4500": flops / ms / 1e9 / 4500, "weight_gbs": wbytes / ms / 1e6,
-                      "cfg": vars(a)}))
+    out = {"ms": ms, "tok_per_s": T / ms * 1e3, "tflops": flops / ms / 1e9,
+           "frac_fp8_4500": flops / ms / 1e9 / 4500, "weight_gbs": wbytes / ms / 1e6, "cfg": vars(a)}
+    import os
+    if int(os.environ.get("HPC_B200_MOE_DEBUG", "0")) & 8:
+        # per-CTA counters of the MMA threads (last Gate-Up and Down launches)
+        import ctypes
+        import numpy as np
+        buf = np.zeros((2, 256, 4), dtype=np.int64)
+        hpc._ffi.lib.hpc_group_gemm_debug_counters.restype = ctypes.c_int
+        hpc._ffi.lib.hpc_group_gemm_debug_counters.argtypes = [ctypes.c_void_p]
+        hpc._ffi.check(hpc._ffi.lib.hpc_group_gemm_debug_counters(buf.ctypes.data), "debug counters")
+        for name, b in (("gate_up", buf[0]), ("down", buf[1])):
+            b = b[b[:, 1] > 0]
+            out[name] = {"ctas": int(len(b)), "cycles_per_kblock": float((b[:, 0] / b[:, 1]).mean()),
+                         "kblocks_per_cta": float(b[:, 1].mean()), "tiles_per_cta": float(b[:, 3].mean()),
+                         "sm_clock_mhz": float((b[:, 0] / b[:, 2]).mean() * 1e3),
+                         "busy_ms_mean": float(b[:, 2].mean() / 1e6), "busy_ms_max": float(b[:, 2].max() / 1e6)}
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
