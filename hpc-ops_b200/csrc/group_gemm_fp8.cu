@@ -88,6 +88,18 @@ __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
+// debug & 8: cycles a role spends blocked in a wait (attribution of the pipeline's bubbles)
+#define HPC_TIMED(acc_var, stmt)                 \
+  do {                                           \
+    if (p.debug & 8) {                           \
+      const long long _t0 = clock64();           \
+      stmt;                                      \
+      acc_var += clock64() - _t0;                \
+    } else {                                     \
+      stmt;                                      \
+    }                                            \
+  } while (0)
+
 struct TileInfo {
   int g, mt, nt;
   int row0;    // first row (global) of the tile
@@ -240,6 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t it = 0;
       uint32_t tq = 0;
       TileInfo t;
+      long long w_empty = 0, w_tq = 0;
+      const long long pc0 = clock64();
       // Dynamic scheduler: tiles are claimed from a global counter, so tiles with neighbouring ids
       // (the m-tiles sharing one weight tile) start within a short window on different CTAs and
       // share that weight tile through L2. The id of the next tile is claimed one tile ahead.
@@ -248,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int tile = next_tile;
         const bool valid = decode_tile(sched, tile, t);
         const uint32_t qs = tq % kTileQ;
-        mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1);
+        HPC_TIMED(w_tq, mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1));
         s_tileq[qs] = valid ? tile : -1;
         const int nb0 = kFused ? t.nt : t.nt * 2;
         int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t s = it % kStages;
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          HPC_TIMED(w_empty, mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1));
           if constexpr (kBlockwise) {
             // Ring of kStages + 2 slots, no "empty" barrier needed: this K block `it` is loaded once
             // stage s is free, i.e. MMA(it - kStages) has completed, which was issued only after the
@@ -304,6 +318,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
         }
       }
+      if (p.debug & 8) {
+        long long* o = p.debug_out + (kFused ? 0 : 16 * 256) + 16 * blockIdx.x;
+        o[8] = clock64() - pc0;
+        o[9] = w_empty;
+        o[10] = w_tq;
+      }
       // the last CTA out re-arms the scheduler for the next launch (no memset between launches:
       // a memset node would break a PDL chain, and a graph replay needs nothing else)
       __threadfence();
@@ -322,14 +342,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t tq = 0;
       uint32_t ntiles = 0;
       unsigned long long g0 = 0;
-      long long c0 = 0;
+      long long c0 = 0, w_full = 0, w_pempty = 0, w_tqm = 0;
       if (p.debug & 8) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
         c0 = clock64();
       }
       while (true) {
         const uint32_t qs = tq % kTileQ;
-        mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
+        HPC_TIMED(w_tqm, mbar_wait(&tq_full[qs], (tq / kTileQ) & 1));
         const int tile = s_tileq[qs];
         mbar_arrive(&tq_empty[qs]);
         tq++;
@@ -339,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t s = it % kStages;
           const bool new_acc = kBlockwise || kb == 0;
           const uint32_t buf = acc_it & 1;
-          mbar_wait(&full[s], (it / kStages) & 1);
-          if (new_acc) mbar_wait(&part_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+          HPC_TIMED(w_full, mbar_wait(&full[s], (it / kStages) & 1));
+          if (new_acc) HPC_TIMED(w_pempty, mbar_wait(&part_empty[buf], ((acc_it >> 1) & 1) ^ 1));
           tc_fence_after();
           const uint64_t ad = adesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
           const uint64_t bd = bdesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
@@ -363,11 +383,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (p.debug & 8) {
         unsigned long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-        long long* o = p.debug_out + (kFused ? 0 : 4 * 256) + 4 * blockIdx.x;
+        long long* o = p.debug_out + (kFused ? 0 : 16 * 256) + 16 * blockIdx.x;
         o[0] = clock64() - c0;
         o[1] = it;
         o[2] = static_cast<long long>(g1 - g0);
         o[3] = ntiles;
+        o[4] = w_full;
+        o[5] = w_pempty;
+        o[6] = w_tqm;
       }
     }
   } else {
@@ -381,9 +404,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t acc_it = 0;
     uint32_t tq = 0;
     TileInfo t;
+    long long w_xs = 0, w_pfull = 0, w_tqe = 0, t_epi = 0;
+    const long long ec0 = clock64();
     while (true) {
       const uint32_t qs = tq % kTileQ;
-      mbar_wait(&tq_full[qs], (tq / kTileQ) & 1);
+      HPC_TIMED(w_tqe, mbar_wait(&tq_full[qs], (tq / kTileQ) & 1));
       const int tile = s_tileq[qs];
       tq++;
       if (tile < 0) {
@@ -407,11 +432,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           // block scales from shared memory (staged by the producer with the operands): no global
           // load latency in this loop
           const uint32_t xsl = acc_it % kXsSlots;
-          mbar_wait(&xs_full[xsl], (acc_it / kXsSlots) & 1);
+          HPC_TIMED(w_xs, mbar_wait(&xs_full[xsl], (acc_it / kXsSlots) & 1));
           const float xs = row_valid ? s_xs[xsl * kBM + row_local] : 0.f;
           const float w0 = ws0[kb], w1 = ws1[kb];
           const uint32_t buf = acc_it & 1;
-          mbar_wait(&part_full[buf], (acc_it >> 1) & 1);
+          HPC_TIMED(w_pfull, mbar_wait(&part_full[buf], (acc_it >> 1) & 1));
           tc_fence_after();
           if (p.debug & 4) {  // diagnostics: no TMEM drain / promotion
             tc_fence_before();
@@ -477,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) mbar_arrive(&tq_empty[qs]);
 
       // ---------------- tile epilogue ----------------
+      const long long te0 = (p.debug & 8) ? clock64() : 0;
       const long long grow = static_cast<long long>(t.row0) + row_local;
       if constexpr (!kFused) {
         if (row_valid) {
@@ -550,6 +576,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         if constexpr (kBlockwise) named_bar_sync(kEpiBar, 256);  // s_amax reuse by the next tile
       }
+      if (p.debug & 8) t_epi += clock64() - te0;
+    }
+    if ((p.debug & 8) && warp == 4 && lane == 0) {
+      long long* o = p.debug_out + (kFused ? 0 : 16 * 256) + 16 * blockIdx.x;
+      o[11] = clock64() - ec0;
+      o[12] = w_xs;
+      o[13] = w_pfull;
+      o[14] = w_tqe;
+      o[15] = t_epi;
     }
   }
 
@@ -558,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static long long* g_dbg_buf[64] = {nullptr};  // HPC_B200_MOE_DEBUG & 8: [2][256][4] int64 per device
+static long long* g_dbg_buf[64] = {nullptr};  // HPC_B200_MOE_DEBUG & 8: [2][256][16] int64 per device
 
 template <bool kBlockwise, bool kFused>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
@@ -578,8 +613,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   pp.debug_out = nullptr;
   if (dbg & 8) {
     if (g_dbg_buf[dev] == nullptr) {
-      HPC_CUDA_CHECK(cudaMalloc(&g_dbg_buf[dev], 2 * 4 * 256 * sizeof(long long)));
-      HPC_CUDA_CHECK(cudaMemset(g_dbg_buf[dev], 0, 2 * 4 * 256 * sizeof(long long)));
+      HPC_CUDA_CHECK(cudaMalloc(&g_dbg_buf[dev], 2 * 16 * 256 * sizeof(long long)));
+      HPC_CUDA_CHECK(cudaMemset(g_dbg_buf[dev], 0, 2 * 16 * 256 * sizeof(long long)));
     }
     pp.debug_out = g_dbg_buf[dev];
   }
@@ -681,11 +716,11 @@ int scale_tile_from_avg(int avg) {
 using namespace b200;  // NOLINT
 
 // diagnostics (HPC_B200_MOE_DEBUG=8): copy the MMA threads' per-CTA counters of the last Gate-Up
-// (fused) and Down / plain launches to the host: out[2][256][4] = {cycles, K blocks, ns, tiles}
+// (fused) and Down / plain launches to the host: out[2][256][16] (see the kernel's debug_out stores)
 extern "C" int hpc_group_gemm_debug_counters(long long* out_host) {
   const int dev = device_slot();
   HPC_REQUIRE(ggemm::g_dbg_buf[dev] != nullptr, "no debug counters recorded (HPC_B200_MOE_DEBUG=8?)");
-  HPC_CUDA_CHECK(cudaMemcpy(out_host, ggemm::g_dbg_buf[dev], 2 * 4 * 256 * sizeof(long long),
+  HPC_CUDA_CHECK(cudaMemcpy(out_host, ggemm::g_dbg_buf[dev], 2 * 16 * 256 * sizeof(long long),
                             cudaMemcpyDeviceToHost));
   return HPC_OK;
 }

@@ -3,6 +3,7 @@
 Implemented in this build (sm_100a):
   * attention_decode_fp8            — quant_type QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR and
                                       QPERTOKEN_PERHEAD_KPERTOKEN_PERHEAD_VPERHEAD (in-cache k scales)
+  * attention_with_kvcache_blocksparse_prefill_fp8 / attention_with_kvcache_prefill_fp8 (dense)
   * get_attention_decode_task_workspace / assign_attention_decode_task (CPU and CUDA)
   * print_attention_decode_task
 The host side does what the reference's torch entry does (validation, scratch allocation, stride
@@ -250,6 +251,22 @@ _ops.define(
     "Tensor? block_mask, Tensor? output) -> (Tensor)")
 _ops.impl("attention_with_kvcache_blocksparse_prefill_fp8", _blocksparse_prefill_impl, "CUDA")
 
+def _dense_prefill_fp8_impl(q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids,
+                            seqlens_kvcache, max_seqlens_q, quant_type, output):
+    # reference src/attention/entry.cc:152-264: the dense path is the block-sparse kernel without
+    # a mask (the reference itself instantiates it with kHasMask=false, hpc/attention.py:270-271)
+    return _blocksparse_prefill_impl(q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q,
+                                     block_ids, seqlens_kvcache, max_seqlens_q, quant_type, None,
+                                     output)
+
+
+_ops.define(
+    "attention_with_kvcache_prefill_fp8(Tensor q, Tensor kcache, Tensor vcache,"
+    "Tensor qscale, Tensor kscale, Tensor vscale, Tensor cu_seqlens_q,"
+    "Tensor block_ids, Tensor num_seq_kvcache, int max_seqlens_q, int quant_type,"
+    "Tensor? output) -> (Tensor)")
+_ops.impl("attention_with_kvcache_prefill_fp8", _dense_prefill_fp8_impl, "CUDA")
+
 _ops.define(
     "attention_decode_fp8(Tensor q, Tensor! kcache, Tensor! vcache, Tensor block_ids, Tensor "
     "num_seq_kvcache, Tensor qscale, Tensor kscale, Tensor vscale, int mtp, bool "
@@ -267,6 +284,29 @@ _ops.impl("assign_attention_decode_task", _assign_task_cuda, "CUDA")
 # --------------------------------------------------------------------------------------------
 # public API (signatures of reference hpc/attention.py)
 # --------------------------------------------------------------------------------------------
+def attention_with_kvcache_prefill_fp8(
+    q: Tensor,
+    kcache: Tensor,
+    vcache: Tensor,
+    qscale: Tensor,
+    kscale: Tensor,
+    vscale: Tensor,
+    cu_seqlens_q: Tensor,
+    block_ids: Tensor,
+    seqlens_kvcache: Tensor,
+    max_seqlens_q: int,
+    quant_type: QuantType = QuantType.QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR,
+    output: Tensor = None,
+) -> Tensor:
+    """Dense causal prefill over the paged FP8 KV cache (contract of reference
+    hpc/attention.py:148-250): the last `seqlens_q[b]` tokens of each request attend to all
+    `seqlens_kvcache[b]` cached tokens causally. Same tensors as
+    `attention_with_kvcache_blocksparse_prefill_fp8` without a block mask; both quant schemes."""
+    return torch.ops.hpc.attention_with_kvcache_prefill_fp8(
+        q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids, seqlens_kvcache,
+        max_seqlens_q, quant_type.value, output)
+
+
 def attention_with_kvcache_blocksparse_prefill_fp8(
     q: Tensor,
     kcache: Tensor,
@@ -437,6 +477,14 @@ def print_attention_decode_task(task_map: Tensor) -> None:
 @torch.library.register_fake("hpc::attention_with_kvcache_blocksparse_prefill_fp8")
 def _blocksparse_prefill_fake(q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids,
                               num_seq_kvcache, max_seqlens_q, quant_type, block_mask, output):
+    if output is not None:
+        return output
+    return torch.empty((q.size(0), q.size(1), vcache.size(3)), dtype=torch.bfloat16, device=q.device)
+
+
+@torch.library.register_fake("hpc::attention_with_kvcache_prefill_fp8")
+def _dense_prefill_fp8_fake(q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids,
+                            num_seq_kvcache, max_seqlens_q, quant_type, output):
     if output is not None:
         return output
     return torch.empty((q.size(0), q.size(1), vcache.size(3)), dtype=torch.bfloat16, device=q.device)

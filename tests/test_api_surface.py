@@ -13,7 +13,7 @@ REF = Path("/root/reference")
 
 IN_SCOPE_OPS = [
     "assign_attention_decode_task", "attention_decode_fp8",
-    "attention_with_kvcache_blocksparse_prefill_fp8",
+    "attention_with_kvcache_blocksparse_prefill_fp8", "attention_with_kvcache_prefill_fp8",
     "fuse_moe", "fuse_moe_pertensor_fp8", "fuse_moe_blockwise", "fuse_moe_blockwise_fp8",
     "count_and_gather", "reduce",
     "group_gemm_fp8", "group_gemm_pertensor_fp8", "group_gemm_blockwise_fp8", "reformat_x_scale",
@@ -26,7 +26,8 @@ IN_SCOPE_OPS = [
 
 PUBLIC_FUNCS = [
     "QuantType", "assign_attention_decode_task", "attention_decode_fp8",
-    "attention_with_kvcache_blocksparse_prefill_fp8", "get_attention_decode_task_workspace",
+    "attention_with_kvcache_blocksparse_prefill_fp8", "attention_with_kvcache_prefill_fp8",
+    "get_attention_decode_task_workspace",
     "print_attention_decode_task",
     "count_and_gather", "fuse_moe", "fuse_moe_blockwise", "fuse_moe_blockwise_fp8",
     "fuse_moe_pertensor_fp8", "reduce",
@@ -81,4 +82,4 @@ def test_schemas_match_reference(hpc):
         want = _canon("hpc::" + ref[name])
         assert mine == want, f"{name}:\n  mine {mine}\n  ref  {want}"
         checked += 1
-    assert checked >= 18
+    assert checked >= 19

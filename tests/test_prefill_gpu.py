@@ -65,6 +65,27 @@ def test_blocksparse_prefill_ragged_and_chunked(hpc, kpt):
     _check(_run(hpc, d, kpt), _oracle(d, kpt), f"ragged dense kpt={kpt}")
 
 
+@pytest.mark.parametrize("kpt", [False, True])
+@pytest.mark.parametrize("num_seq_q", [100, 500, 1500, 3904])
+@pytest.mark.parametrize("layout", ["nhd", "hnd"])
+def test_dense_kvcache_prefill_fp8(hpc, kpt, num_seq_q, layout):
+    """hpc.attention_with_kvcache_prefill_fp8: grid of reference
+    tests/test_attention_with_kvcache_q*_prefill_fp8.py:92-101 (B=4 -> 2 here, kv 3904, q chunk of
+    100..3904 tokens at the end of the cache), tolerance atol=0.05 (:233)."""
+    B, S = 2, 3904
+    d = op.make_inputs([num_seq_q] * B, [S] * B, 4, 1, None, kpt, layout=layout, seed=10086)
+    c = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    qt = (hpc.QuantType.QPERTOKEN_PERHEAD_KPERTOKEN_PERHEAD_VPERHEAD if kpt
+          else hpc.QuantType.QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR)
+    my = hpc.attention_with_kvcache_prefill_fp8(
+        c["q"], c["kcache"], c["vcache"], c["qscale"], c["kscale"], c["vscale"], c["cu_seqlens_q"],
+        c["block_ids"], c["seqlens_kv"], d["max_q"], quant_type=qt)
+    gt = _oracle(d, kpt)
+    my, gt = my.float().cpu(), gt.float()
+    assert torch.isfinite(my).all()
+    assert torch.allclose(my, gt, atol=0.05), (my - gt).abs().max()
+
+
 def test_blocksparse_prefill_short_mask_width(hpc):
     """Kb shorter than the causal extent: exactly one extra tile (index Kb) is visited
     (reference kernels.cuh:2195-2216)."""

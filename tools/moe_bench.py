@@ -72,16 +72,25 @@ def main():
         # per-CTA counters of the MMA threads (last Gate-Up and Down launches)
         import ctypes
         import numpy as np
-        buf = np.zeros((2, 256, 4), dtype=np.int64)
+        buf = np.zeros((2, 256, 16), dtype=np.int64)
         hpc._ffi.lib.hpc_group_gemm_debug_counters.restype = ctypes.c_int
         hpc._ffi.lib.hpc_group_gemm_debug_counters.argtypes = [ctypes.c_void_p]
         hpc._ffi.check(hpc._ffi.lib.hpc_group_gemm_debug_counters(buf.ctypes.data), "debug counters")
         for name, b in (("gate_up", buf[0]), ("down", buf[1])):
-            b = b[b[:, 1] > 0]
-            out[name] = {"ctas": int(len(b)), "cycles_per_kblock": float((b[:, 0] / b[:, 1]).mean()),
-                         "kblocks_per_cta": float(b[:, 1].mean()), "tiles_per_cta": float(b[:, 3].mean()),
-                         "sm_clock_mhz": float((b[:, 0] / b[:, 2]).mean() * 1e3),
-                         "busy_ms_mean": float(b[:, 2].mean() / 1e6), "busy_ms_max": float(b[:, 2].max() / 1e6)}
+            b = b[b[:, 1] > 0].astype(np.float64)
+            kb = b[:, 1]
+            out[name] = {
+                "cycles_per_kblock": float((b[:, 0] / kb).mean()),
+                "sm_clock_mhz": float((b[:, 0] / b[:, 2]).mean() * 1e3),
+                "busy_ms": float(b[:, 2].mean() / 1e6), "tiles_per_cta": float(b[:, 3].mean()),
+                # cycles per K block each role spends blocked
+                "mma_wait_full": float((b[:, 4] / kb).mean()), "mma_wait_acc_free": float((b[:, 5] / kb).mean()),
+                "mma_wait_tileq": float((b[:, 6] / kb).mean()),
+                "prod_wait_stage": float((b[:, 9] / kb).mean()), "prod_wait_tileq": float((b[:, 10] / kb).mean()),
+                "epi_total": float((b[:, 11] / kb).mean()), "epi_wait_xs": float((b[:, 12] / kb).mean()),
+                "epi_wait_acc_ready": float((b[:, 13] / kb).mean()), "epi_wait_tileq": float((b[:, 14] / kb).mean()),
+                "epi_tile_epilogue": float((b[:, 15] / kb).mean()),
+                "epi_tile_epilogue_cycles_per_tile": float((b[:, 15] / b[:, 3]).mean())}
     print(json.dumps(out))
 
 

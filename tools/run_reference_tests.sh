@@ -9,7 +9,7 @@ files=${@:-"test_attention_decode_qpertoken_perhead_kvpertensor_fp8.py test_atte
 : > "$out"
 for f in $files; do
   if [ ! -f baseline/_ref/tests/$f ]; then echo "$f: not staged" >> "$out"; continue; fi
-  r=$( cd baseline/_ref/tests && timeout $tmo python -m pytest $f -q -x --no-header -p no:cacheprovider 2>&1 | tail -3 | tr '\n' ' ' )
+  r=$( cd baseline/_ref/tests && timeout $tmo python -m pytest $f -q --no-header -p no:cacheprovider 2>&1 | tail -3 | tr '\n' ' ' )
   echo "$f: $r" >> "$out"
 done
 cat "$out"
