@@ -191,12 +191,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t qcnt = 0;   // task counter for the Q double buffer
     Task t;
     for (const int* row = bin; load_task(row, t); row += kTaskStride) {
-      if (lane == 0) {
+      // The whole warp walks the task list with warp-uniform values and ONE elected lane issues:
+      // operands of TMA / mbarrier instructions live in uniform registers, and values the compiler
+      // cannot prove uniform (anything loaded from memory) would make it wrap each instruction in an
+      // elect + R2UR.BROADCAST loop (~70 cycles apiece).
+      t.ihead_kv = __shfl_sync(0xffffffffu, t.ihead_kv, 0);
+      t.ibatch = __shfl_sync(0xffffffffu, t.ibatch, 0);
+      t.num_tile_kv = __shfl_sync(0xffffffffu, t.num_tile_kv, 0);
+      {
         const int qb = qcnt & 1;
         mbar_wait(&q_empty[qb], ((qcnt >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qb], p.num_seq_q * p.group * kD);
-        tma_load_3d(q_smem + qb * 4096, &tmap_q, &q_full[qb], 0, t.ihead_kv * p.group,
-                    t.ibatch * p.num_seq_q);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[qb], p.num_seq_q * p.group * kD);
+          tma_load_3d(q_smem + qb * 4096, &tmap_q, &q_full[qb], 0, t.ihead_kv * p.group,
+                      t.ibatch * p.num_seq_q);
+        }
+        __syncwarp();
       }
       qcnt++;
       const int nblk = (t.num_seqkv + kPage - 1) / kPage;
@@ -215,9 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int tt = 0; tt < gt; tt++) {
           const int id0 = __shfl_sync(0xffffffffu, my_id, 2 * tt);
           const int id1 = __shfl_sync(0xffffffffu, my_id, 2 * tt + 1);
-          if (lane == 0) {
-            const uint32_t st = n % kNumStages;
-            mbar_wait(&stage_empty[st], ((n / kNumStages) & 1) ^ 1);
+          const uint32_t st = n % kNumStages;
+          mbar_wait(&stage_empty[st], ((n / kNumStages) & 1) ^ 1);
+          if (elect_one()) {
             uint8_t* dst = stages + st * kStageBytes;
             mbar_arrive_expect_tx(&k_full[st], kSlotBytes);
             tma_load_4d_hint(dst, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_stream);
@@ -229,13 +239,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_4d_hint(dst + kSlotBytes + kSlotBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2,
                              id1, pol_stream);
           }
+          __syncwarp();
           n++;
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== tcgen05 issuer (one thread) ==============================
-    if (lane == 0) {
+    // =========================== tcgen05 issuer (whole warp, one elected lane issues) ========
+    {
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform copy
       constexpr uint32_t idesc_qk = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, NQ, kFmtE4M3, kFmtE4M3, 1, 1);
       // Descriptor templates; per tile only the 14-bit start-address field (units of 16 B) moves.
@@ -258,12 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint64_t ad = vdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
         const uint64_t bd = pdesc0 + static_cast<uint64_t>(buf * (L::kPBytes >> 4));
         const uint32_t d = tmem_base + 2 * NQ + buf * NQ;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          umma_f8(d, ad + k * (4096 >> 4), bd + k * (512 >> 4), idesc_pv, k > 0);
+          for (int k = 0; k < 4; k++) {
+            umma_f8(d, ad + k * (4096 >> 4), bd + k * (512 >> 4), idesc_pv, k > 0);
+          }
+          umma_commit(&o_full[buf]);  // the softmax warps wait for this one: first
+          umma_commit(&stage_empty[st]);
         }
-        umma_commit(&stage_empty[st]);
-        umma_commit(&o_full[buf]);
+        __syncwarp();
       };
 
       uint32_t n = 0;
@@ -273,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int qb = qcnt & 1;
         mbar_wait(&q_full[qb], (qcnt >> 1) & 1);
         const uint64_t bd = qdesc0 + static_cast<uint64_t>(qb * (4096 >> 4));
-        const int ntiles = t.num_tile_kv;
+        const int ntiles = __shfl_sync(0xffffffffu, t.num_tile_kv, 0);
         for (int tt = 0; tt < ntiles; tt++) {
           const uint32_t st = n % kNumStages;
           const uint32_t buf = n & 1;
@@ -281,12 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint64_t ad = kdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
           const uint32_t d = tmem_base + buf * NQ;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            umma_f8(d, ad + k * (32 >> 4), bd + k * (32 >> 4), idesc_qk, k > 0);
+            for (int k = 0; k < 4; k++) {
+              umma_f8(d, ad + k * (32 >> 4), bd + k * (32 >> 4), idesc_qk, k > 0);
+            }
+            umma_commit(&s_full[buf]);
+            if (tt == ntiles - 1) umma_commit(&q_empty[qb]);
           }
-          umma_commit(&s_full[buf]);
-          if (tt == ntiles - 1) umma_commit(&q_empty[qb]);
+          __syncwarp();
           if (n > 0) issue_pv(n - 1);
           n++;
         }

@@ -243,8 +243,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // =========================== TMA producer ==========================================
+      // The whole warp runs this loop with warp-uniform values (tile fields are broadcast with
+      // shfl) and ONE elected lane issues: TMA / mbarrier / tcgen05 instructions take their operands
+      // from uniform registers, and for values the compiler cannot prove uniform it wraps every
+      // such instruction in an elect + R2UR.BROADCAST "waterfall" loop (~70 cycles per instruction:
+      // measured 600-700 cycles of issue work per K block with single-lane roles).
       // A rows of a group are re-read by every n-tile -> keep them in L2. Weight tiles are shared
       // by the 2-3 m-tiles of the same (group, n-tile), which run on neighbouring CTAs at about
       // the same time -> default policy (evict_first made every m-tile re-read HBM: 2.35x traffic).
@@ -257,29 +262,43 @@ __global__ void __launch_bounds__(kThreads, 1)
       // Dynamic scheduler: tiles are claimed from a global counter, so tiles with neighbouring ids
       // (the m-tiles sharing one weight tile) start within a short window on different CTAs and
       // share that weight tile through L2. The id of the next tile is claimed one tile ahead.
-      int next_tile = atomicAdd(p.tile_counter, 1);
+      auto claim = [&]() -> int {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(p.tile_counter, 1);
+        return __shfl_sync(0xffffffffu, v, 0);
+      };
+      int next_tile = claim();
       while (true) {
         const int tile = next_tile;
-        const bool valid = decode_tile(sched, tile, t);
+        bool valid = decode_tile(sched, tile, t);
+        valid = __shfl_sync(0xffffffffu, static_cast<int>(valid), 0) != 0;
+        t.g = __shfl_sync(0xffffffffu, t.g, 0);
+        t.nt = __shfl_sync(0xffffffffu, t.nt, 0);
+        t.row0 = __shfl_sync(0xffffffffu, t.row0, 0);
+        t.nvalid = __shfl_sync(0xffffffffu, t.nvalid, 0);
+        t.scol0 = __shfl_sync(0xffffffffu, t.scol0, 0);
         const uint32_t qs = tq % kTileQ;
         HPC_TIMED(w_tq, mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1));
-        s_tileq[qs] = valid ? tile : -1;
         const int nb0 = kFused ? t.nt : t.nt * 2;
         int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
         if (nb1 >= nblk_per_group) nb1 = nb0;
-        if (kBlockwise && valid) {
-          // the tile's weight scales (KB floats for each 128-column half) travel with its queue slot
-          const uint32_t bytes = static_cast<uint32_t>(p.kpad4) * 4u;
-          mbar_arrive_expect_tx(&tq_full[qs], 2 * bytes);
-          const float* ws = p.wscale + static_cast<long long>(t.g) * nblk_per_group * p.kpad4;
-          bulk_load_1d(s_ws + (qs * 2 + 0) * kMaxKB, ws + static_cast<long long>(nb0) * p.kpad4, bytes, &tq_full[qs]);
-          bulk_load_1d(s_ws + (qs * 2 + 1) * kMaxKB, ws + static_cast<long long>(nb1) * p.kpad4, bytes, &tq_full[qs]);
-        } else {
-          mbar_arrive(&tq_full[qs]);
+        if (elect_one()) {
+          s_tileq[qs] = valid ? tile : -1;
+          if (kBlockwise && valid) {
+            // the tile's weight scales (KB floats for each 128-column half) travel with its queue slot
+            const uint32_t bytes = static_cast<uint32_t>(p.kpad4) * 4u;
+            mbar_arrive_expect_tx(&tq_full[qs], 2 * bytes);
+            const float* ws = p.wscale + static_cast<long long>(t.g) * nblk_per_group * p.kpad4;
+            bulk_load_1d(s_ws + (qs * 2 + 0) * kMaxKB, ws + static_cast<long long>(nb0) * p.kpad4, bytes, &tq_full[qs]);
+            bulk_load_1d(s_ws + (qs * 2 + 1) * kMaxKB, ws + static_cast<long long>(nb1) * p.kpad4, bytes, &tq_full[qs]);
+          } else {
+            mbar_arrive(&tq_full[qs]);
+          }
         }
+        __syncwarp();
         tq++;
         if (!valid) break;
-        next_tile = atomicAdd(p.tile_counter, 1);
+        next_tile = claim();
         const int nrow0 = kFused ? t.nt * 128 : t.nt * kBN;
         const int nrow1 = kFused ? p.n / 2 + t.nt * 128 : t.nt * kBN + 128;
         // activation scales of the tile's rows: 16-byte granules covering the valid rows
@@ -289,36 +308,40 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
           HPC_TIMED(w_empty, mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1));
-          if constexpr (kBlockwise) {
-            // Ring of kStages + 2 slots, no "empty" barrier needed: this K block `it` is loaded once
-            // stage s is free, i.e. MMA(it - kStages) has completed, which was issued only after the
-            // epilogue finished with K block it - kStages - 2 -- the previous user of this slot.
-            const uint32_t xsl = it % kXsSlots;
-            mbar_arrive_expect_tx(&xs_full[xsl], xs_bytes);
-            bulk_load_1d(s_xs + xsl * kBM, p.xscale_t + static_cast<long long>(kb) * p.m_pad + t.scol0,
-                         xs_bytes, &xs_full[xsl]);
-          }
-          if (p.debug & 3) {  // diagnostics: leave out the weight (1) / activation (2) tile loads
-            const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes);
-            if (bytes == 0) {
-              mbar_arrive(&full[s]);
-            } else {
-              mbar_arrive_expect_tx(&full[s], bytes);
+          if (elect_one()) {
+            if constexpr (kBlockwise) {
+              // Ring of kStages + 2 slots, no "empty" barrier needed: this K block `it` is loaded
+              // once stage s is free, i.e. MMA(it - kStages) has completed, which was issued only
+              // after the epilogue finished with K block it - kStages - 2 -- the previous user of
+              // this slot.
+              const uint32_t xsl = it % kXsSlots;
+              mbar_arrive_expect_tx(&xs_full[xsl], xs_bytes);
+              bulk_load_1d(s_xs + xsl * kBM, p.xscale_t + static_cast<long long>(kb) * p.m_pad + t.scol0,
+                           xs_bytes, &xs_full[xsl]);
             }
-            if (!(p.debug & 2)) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
-            if (!(p.debug & 1)) {
+            if (p.debug & 3) {  // diagnostics: leave out the weight (1) / activation (2) tile loads
+              const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes);
+              if (bytes == 0) {
+                mbar_arrive(&full[s]);
+              } else {
+                mbar_arrive_expect_tx(&full[s], bytes);
+              }
+              if (!(p.debug & 2)) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
+              if (!(p.debug & 1)) {
+                tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
+                tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+              }
+            } else {
+              mbar_arrive_expect_tx(&full[s], kStageBytes);
+              tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
               tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
               tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
             }
-            continue;
           }
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
-          tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
-          tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+          __syncwarp();
         }
       }
-      if (p.debug & 8) {
+      if ((p.debug & 8) && lane == 0) {
         long long* o = p.debug_out + (kFused ? 0 : 16 * 256) + 16 * blockIdx.x;
         o[8] = clock64() - pc0;
         o[9] = w_empty;
@@ -326,15 +349,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       // the last CTA out re-arms the scheduler for the next launch (no memset between launches:
       // a memset node would break a PDL chain, and a graph replay needs nothing else)
-      __threadfence();
-      if (atomicAdd(p.tile_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-        p.tile_counter[0] = 0;
-        p.tile_counter[1] = 0;
+      if (lane == 0) {
         __threadfence();
+        if (atomicAdd(p.tile_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+          p.tile_counter[0] = 0;
+          p.tile_counter[1] = 0;
+          __threadfence();
+        }
       }
-    } else if (warp == 1 && lane == 0) {
-      // =========================== tcgen05 issuer =========================================
+    } else if (warp == 1) {
+      // =========================== tcgen05 issuer (whole warp, one elected lane issues) =======
       constexpr uint32_t idesc = make_idesc(kBM, kBN, kFmtE4M3, kFmtE4M3, 0, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t adesc0 = make_smem_desc(smem_u32(stages), 16, 1024, kLayoutSW128);
       const uint64_t bdesc0 = make_smem_desc(smem_u32(stages) + kABytes, 16, 1024, kLayoutSW128);
       uint32_t it = 0;   // K-block counter (smem ring)
@@ -350,8 +376,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       while (true) {
         const uint32_t qs = tq % kTileQ;
         HPC_TIMED(w_tqm, mbar_wait(&tq_full[qs], (tq / kTileQ) & 1));
-        const int tile = s_tileq[qs];
-        mbar_arrive(&tq_empty[qs]);
+        const int tile = __shfl_sync(0xffffffffu, s_tileq[qs], 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tq_empty[qs]);
         tq++;
         if (tile < 0) break;
         ntiles++;
@@ -364,23 +391,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint64_t ad = adesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
           const uint64_t bd = bdesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
-          const uint32_t d = tmem_base + buf * kBN;
+          const uint32_t d = tmem_u + buf * kBN;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            umma_f8(d, ad + k * 2, bd + k * 2, idesc, (k > 0) || !new_acc);
+            for (int k = 0; k < 4; k++) {
+              umma_f8(d, ad + k * 2, bd + k * 2, idesc, (k > 0) || !new_acc);
+            }
+            // The accumulator hand-over is the critical path (MMA -> drain -> next MMA into this
+            // buffer); the stage release is not (the producer runs kStages ahead). Commits are
+            // processed in order, so "accumulator ready" goes first (tools/umma_rate.py: 725 ->
+            // 563 cycles per K block).
+            if (kBlockwise || kb == KB - 1) umma_commit(&part_full[buf]);
+            umma_commit(&empty[s]);
           }
-          // The accumulator hand-over is the critical path (MMA -> drain -> next MMA into this
-          // buffer); the stage release is not (the producer runs kStages ahead). Commits are
-          // processed in order, so "accumulator ready" goes first (measured with
-          // tools/umma_rate.py: 725 -> 563 cycles per K block).
-          if (kBlockwise || kb == KB - 1) {
-            umma_commit(&part_full[buf]);
-            acc_it++;
-          }
-          umma_commit(&empty[s]);
+          __syncwarp();
+          if (kBlockwise || kb == KB - 1) acc_it++;
         }
       }
-      if (p.debug & 8) {
+      if ((p.debug & 8) && lane == 0) {
         unsigned long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
         long long* o = p.debug_out + (kFused ? 0 : 16 * 256) + 16 * blockIdx.x;

@@ -161,12 +161,17 @@ __global__ void __launch_bounds__(kThreads, 2)
           }
         }
         __syncwarp();
-        if (lane == 0) {
+        // warp-uniform copies of what the elected lane's TMA instructions take as operands (the
+        // compiler cannot prove values loaded from memory uniform and would wrap every TMA /
+        // mbarrier instruction in an elect + R2UR.BROADCAST loop)
+        const int u_hq = __shfl_sync(0xffffffffu, k.hq, 0);
+        const int u_q0 = __shfl_sync(0xffffffffu, k.q0, 0);
+        if (elect_one()) {
           s_work[0] = alive ? w : -1;
           s_work[1] = nact;
           if (alive) {
             mbar_arrive_expect_tx(q_full, kTileBytes);
-            tma_load_3d(q_smem, &tmap_q, q_full, 0, k.hq, k.q0);
+            tma_load_3d(q_smem, &tmap_q, q_full, 0, u_hq, u_q0);
           } else {
             mbar_arrive(q_full);
           }
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         item++;
         if (!alive) break;
         // ---- K/V tiles of the active list ----
-        const int hkv = k.hq / p.group;
+        const int hkv = u_hq / p.group;
         const int nblk = (k.seq_kv + kPage - 1) / kPage;
         const int* ids = p.block_ids + static_cast<long long>(k.b) * p.max_blocks;
         const int kc1 = p.k_head_first ? hkv : 0, kc2 = p.k_head_first ? 0 : hkv;
@@ -193,10 +198,10 @@ __global__ void __launch_bounds__(kThreads, 2)
           for (int t = 0; t < cnt; t++) {
             const int id0 = __shfl_sync(0xffffffffu, id, 2 * t);
             const int id1 = __shfl_sync(0xffffffffu, id, 2 * t + 1);
-            if (lane == 0) {
-              const uint32_t st = n % kStages;
-              const uint32_t ph = ((n / kStages) & 1) ^ 1;
-              mbar_wait(&k_empty[st], ph);  // QK(n - 2) finished
+            const uint32_t st = n % kStages;
+            const uint32_t ph = ((n / kStages) & 1) ^ 1;
+            mbar_wait(&k_empty[st], ph);  // QK(n - 2) finished
+            if (elect_one()) {
               uint8_t* kd8 = k_smem + st * kTileBytes;
               mbar_arrive_expect_tx(&k_full[st], kTileBytes + (kKPerToken ? 512 : 0));
               tma_load_4d_hint(kd8, &tmap_k, &k_full[st], 0, kc1, kc2, id0, pol_kv);
@@ -211,18 +216,23 @@ __global__ void __launch_bounds__(kThreads, 2)
                 bulk_load_1d(kd + 64, s1, 128, &k_full[st]);
                 bulk_load_1d(kd + 96, s1 + p.ks_stride_grp, 128, &k_full[st]);
               }
-              mbar_wait(&v_empty[st], ph);  // PV(n - 2) finished
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[st], ph);  // PV(n - 2) finished
+            if (elect_one()) {
               uint8_t* vd8 = v_smem + st * kTileBytes;
               mbar_arrive_expect_tx(&v_full[st], kTileBytes);
               tma_load_4d_hint(vd8, &tmap_v, &v_full[st], 0, vc1, vc2, id0, pol_kv);
               tma_load_4d_hint(vd8 + kTileBytes / 2, &tmap_v, &v_full[st], 0, vc1, vc2, id1, pol_kv);
             }
+            __syncwarp();
             n++;
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // =========================== tcgen05 issuer (one thread) ============================
+    } else if (warp == 1) {
+      // =========================== tcgen05 issuer (whole warp, one elected lane issues) =======
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform copy
       constexpr uint32_t idesc_qk = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, 128, kFmtE4M3, kFmtE4M3, 0, 1);
       const uint64_t kdesc0 = make_smem_desc(smem_u32(k_smem), 16, 1024, kLayoutSW128);
@@ -236,21 +246,25 @@ __global__ void __launch_bounds__(kThreads, 2)
         if (m > 0) mbar_wait(s_free, (m - 1) & 1);
         tc_fence_after();
         const uint64_t kd = kdesc0 + static_cast<uint64_t>(st * (kTileBytes >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) umma_f8(tmem_base, qdesc + k * 2, kd + k * 2, idesc_qk, k > 0);
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);
-        if (last_of_item) umma_commit(q_empty);  // Q tile / list reusable after this QK
+          for (int k = 0; k < 4; k++) umma_f8(tmem_base, qdesc + k * 2, kd + k * 2, idesc_qk, k > 0);
+          umma_commit(s_full);
+          umma_commit(&k_empty[st]);
+          if (last_of_item) umma_commit(q_empty);  // Q tile / list reusable after this QK
+        }
+        __syncwarp();
       };
       uint32_t n = 0;
       uint32_t item = 0;
       while (true) {
         mbar_wait(q_full, item & 1);
-        const int w = s_work[0];
-        const int nact = s_work[1];
+        const int w = __shfl_sync(0xffffffffu, s_work[0], 0);
+        const int nact = __shfl_sync(0xffffffffu, s_work[1], 0);
         if (w < 0) break;
         if (nact == 0) {
-          umma_commit(q_empty);
+          if (elect_one()) umma_commit(q_empty);
+          __syncwarp();
         } else {
           issue_qk(n, nact == 1);
           for (int i = 0; i < nact; i++) {
@@ -260,13 +274,16 @@ __global__ void __launch_bounds__(kThreads, 2)
             mbar_wait(p_full, n & 1);
             tc_fence_after();
             const uint64_t vd = vdesc0 + static_cast<uint64_t>(st * (kTileBytes >> 4));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
-              umma_f8(tmem_base + 128, pdesc + k * 2, vd + k * (4096 >> 4), idesc_pv,
-                      (k > 0) || (i > 0));
+              for (int k = 0; k < 4; k++) {
+                // A = P (K-major, 32 B per MMA); B = V as stored: MN-major, 32 keys = 4096 B per MMA
+                umma_f8(tmem_base + 128, pdesc + k * 2, vd + k * (4096 >> 4), idesc_pv,
+                        (k > 0) || (i > 0));
+              }
+              umma_commit(&v_empty[st]);
             }
-            umma_commit(&v_empty[st]);
+            __syncwarp();
             n++;
           }
         }
