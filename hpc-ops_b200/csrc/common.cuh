@@ -248,6 +248,12 @@ __device__ __forceinline__ void tma_load_4d_hint(void* dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
       : "memory");
 }
+// TMA prefetch of a tile into L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (size multiple of 16 B, 16-B aligned), completes on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes,
                                              uint64_t* bar) {

@@ -46,6 +46,7 @@ constexpr int kEpiBar = 2;
 constexpr int kTileQ = 4;
 constexpr int kXsSlots = kStages + 2;  // activation-scale ring (see the producer)
 constexpr int kMaxKB = 128;            // K blocks per tile whose weight scales are staged (K <= 16384)
+constexpr int kPrefetch = 6;           // L2 prefetch distance of the weight tiles, in K blocks
 
 struct Params {
   const int* seqlens;      // [G] rows per group
@@ -121,7 +122,7 @@ struct Sched {
 // tile queue, TMEM slot
 constexpr int kSmemBytes = kStages * kStageBytes + (kMaxGroups + 4 + 3 * kMaxGroups) * 4 + 256 * 4 +
                            kXsSlots * kBM * 4 + kTileQ * 2 * kMaxKB * 4 +
-                           (2 * kStages + 4 + 2 * kTileQ + kXsSlots) * 8 + kTileQ * 4 + 16;
+                           (2 * kStages + 4 + 2 * kTileQ) * 8 + kTileQ * 4 + 16;
 
 __device__ __forceinline__ bool decode_tile(const Sched& s, int tile, TileInfo& t) {
   if (tile >= s.cu_tiles[s.num_group]) return false;
@@ -167,8 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* part_empty = part_full + 2;
   uint64_t* tq_full = part_empty + 2;   // tile-id queue (kTileQ slots): producer -> consumers
   uint64_t* tq_empty = tq_full + kTileQ;
-  uint64_t* xs_full = tq_empty + kTileQ;  // [kXsSlots]
-  int* s_tileq = reinterpret_cast<int*>(xs_full + kXsSlots);
+  int* s_tileq = reinterpret_cast<int*>(tq_empty + kTileQ);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_tileq + kTileQ);
 
   const int tid = threadIdx.x;
@@ -194,7 +194,6 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&tq_full[i], 1);
       mbar_init(&tq_empty[i], 9);  // MMA thread + 8 epilogue warps
     }
-    for (int i = 0; i < kXsSlots; i++) mbar_init(&xs_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -255,6 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // the same time -> default policy (evict_first made every m-tile re-read HBM: 2.35x traffic).
       const uint64_t pol_a = make_policy_evict_last();
       uint32_t it = 0;
+      uint32_t xsl = 0;  // it % kXsSlots
       uint32_t tq = 0;
       TileInfo t;
       long long w_empty = 0, w_tq = 0;
@@ -309,22 +309,26 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* b_dst = a_dst + kABytes;
           HPC_TIMED(w_empty, mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1));
           if (elect_one()) {
+            uint32_t extra = 0;
             if constexpr (kBlockwise) {
-              // Ring of kStages + 2 slots, no "empty" barrier needed: this K block `it` is loaded
-              // once stage s is free, i.e. MMA(it - kStages) has completed, which was issued only
-              // after the epilogue finished with K block it - kStages - 2 -- the previous user of
-              // this slot.
-              const uint32_t xsl = it % kXsSlots;
-              mbar_arrive_expect_tx(&xs_full[xsl], xs_bytes);
-              bulk_load_1d(s_xs + xsl * kBM, p.xscale_t + static_cast<long long>(kb) * p.m_pad + t.scol0,
-                           xs_bytes, &xs_full[xsl]);
+              // The K block's 128 activation scales ride on the stage's barrier. Ring of kStages + 2
+              // slots with no "empty" barrier: K block `it` is loaded once stage s is free, i.e.
+              // MMA(it - kStages) has completed, which was issued only after the epilogue finished
+              // with K block it - kStages - 2 -- the previous user of this slot. The epilogue reads
+              // the slot after it has seen the K block's accumulator (committed after the MMA, which
+              // was issued after `full[s]` completed): no barrier wait of its own.
+              extra = xs_bytes;
             }
             if (p.debug & 3) {  // diagnostics: leave out the weight (1) / activation (2) tile loads
-              const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes);
+              const uint32_t bytes = ((p.debug & 1) ? 0 : kBBytes) + ((p.debug & 2) ? 0 : kABytes) + extra;
               if (bytes == 0) {
                 mbar_arrive(&full[s]);
               } else {
                 mbar_arrive_expect_tx(&full[s], bytes);
+              }
+              if constexpr (kBlockwise) {
+                bulk_load_1d(s_xs + xsl * kBM, p.xscale_t + static_cast<long long>(kb) * p.m_pad + t.scol0,
+                             xs_bytes, &full[s]);
               }
               if (!(p.debug & 2)) tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
               if (!(p.debug & 1)) {
@@ -332,12 +336,24 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
               }
             } else {
-              mbar_arrive_expect_tx(&full[s], kStageBytes);
+              mbar_arrive_expect_tx(&full[s], kStageBytes + extra);
+              if constexpr (kBlockwise) {
+                bulk_load_1d(s_xs + xsl * kBM, p.xscale_t + static_cast<long long>(kb) * p.m_pad + t.scol0,
+                             xs_bytes, &full[s]);
+              }
               tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
               tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
               tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
+              // Weight tiles stream from HBM (~2 us under load) but a stage is requested only
+              // ~3 K blocks (~2 us) before its MMA: pull the tiles kPrefetch K blocks ahead into L2
+              // so that the stage load itself is an L2 hit.
+              if (kb + kPrefetch < KB && !(p.debug & 16)) {
+                tma_prefetch_l2_3d(&tmap_b, (kb + kPrefetch) * kBK, nrow0, t.g);
+                tma_prefetch_l2_3d(&tmap_b, (kb + kPrefetch) * kBK, nrow1, t.g);
+              }
             }
           }
+          if (++xsl == kXsSlots) xsl = 0;
           __syncwarp();
         }
       }
@@ -430,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
 
     uint32_t acc_it = 0;
+    uint32_t xsl = 0;  // acc_it % kXsSlots (blockwise)
     uint32_t tq = 0;
     TileInfo t;
     long long w_xs = 0, w_pfull = 0, w_tqe = 0, t_epi = 0;
@@ -457,15 +474,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         const float* ws0 = s_ws + (qs * 2 + 0) * kMaxKB;
         const float* ws1 = s_ws + (qs * 2 + 1) * kMaxKB;
         for (int kb = 0; kb < KB; kb++, acc_it++) {
-          // block scales from shared memory (staged by the producer with the operands): no global
-          // load latency in this loop
-          const uint32_t xsl = acc_it % kXsSlots;
-          HPC_TIMED(w_xs, mbar_wait(&xs_full[xsl], (acc_it / kXsSlots) & 1));
-          const float xs = row_valid ? s_xs[xsl * kBM + row_local] : 0.f;
-          const float w0 = ws0[kb], w1 = ws1[kb];
           const uint32_t buf = acc_it & 1;
           HPC_TIMED(w_pfull, mbar_wait(&part_full[buf], (acc_it >> 1) & 1));
           tc_fence_after();
+          // block scales from shared memory (staged by the producer with the operands of this K
+          // block, which the MMA has consumed by now): no global load latency, no extra barrier
+          const float xs = row_valid ? s_xs[xsl * kBM + row_local] : 0.f;
+          const float w0 = ws0[kb], w1 = ws1[kb];
+          if (++xsl == kXsSlots) xsl = 0;
           if (p.debug & 4) {  // diagnostics: no TMEM drain / promotion
             tc_fence_before();
             __syncwarp();

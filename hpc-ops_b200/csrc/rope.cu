@@ -1,0 +1,306 @@
+// RoPE (NeoX halves) + optional per-head RMSNorm + paged KV-cache store, bf16 and FP8 — the step
+// before attention: it writes the paged cache layout the decode / prefill kernels read.
+// B200 build written from scratch; semantics of reference src/rope/rope.cu:99-418 (bf16) and
+// :420-850 (fp8), launcher contract of src/rope/rope.h:15-38.
+//
+// HBM-bound streaming kernel: one warp per (token row, head) item, where the heads of a row are
+// [q heads | k heads | v heads] exactly as they lie in the packed qkv row. A lane owns dims
+// {2l, 2l+1} of the lower half and the matching dims of the upper half (the NeoX rotation pairs),
+// i.e. 4-byte coalesced accesses (128 B per warp per half), fp32 math, warp-shuffle reductions for
+// the RMS and the dynamic Q amax. The warp of a request's LAST token also zeroes the unused tail
+// of that request's last cache page (the "unused slots are zero" contract of the attention ops).
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace b200 {
+namespace rope {
+
+constexpr int kWarpsPerBlock = 8;
+
+struct Params {
+  void* out_q;
+  void* kcache;
+  void* vcache;
+  void* out_k;            // optional bypass: [rows, Hkv, Dqk] instead of the cache
+  void* out_v;
+  int* split_k_flag;      // fp8: [num_req, Hkv], zeroed here
+  float* q_scale;         // fp8 dynamic: prefill [num_req, Hq, max_seqlen_aligned], decode [rows, Hq]
+  const __nv_bfloat16* qkv;
+  const float* cos_sin;   // [max_pos, Dqk]: cos | sin halves
+  const int* seqlen;      // [num_req] total length incl. the new tokens
+  const int* q_index;     // [num_req + 1]
+  const int* kv_indices;  // [num_req, max_blocks]
+  const float* q_norm_w;
+  const float* k_norm_w;
+  const float* k_scale;
+  const float* v_scale;
+  const float* q_scale_inv;
+  float upper_max;
+  int max_seqlen_aligned;
+  long long kcache_block_stride, vcache_block_stride;  // elements
+  int num_req, max_blocks, block_size, num_rows, hq, hkv, dqk, dv;
+  int is_prefill, norm_policy, quant_policy;
+};
+
+template <typename T>
+__device__ __forceinline__ void store2(T* dst, float a, float b);
+template <>
+__device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
+}
+template <>
+__device__ __forceinline__ void store2<uint8_t>(uint8_t* dst, float a, float b) {
+  *reinterpret_cast<uint16_t*>(dst) = cvt_e4m3x2(a, b);
+}
+
+// kFp8: caches / out_q are e4m3 (uint8_t), else bf16. kHalf = Dqk / 2 handled in chunks of 64 dims.
+template <bool kFp8>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    rope_norm_store_kv_kernel(const Params p) {
+  using OutT = typename std::conditional<kFp8, uint8_t, __nv_bfloat16>::type;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int heads = p.hq + 2 * p.hkv;
+  const long long items = static_cast<long long>(p.num_rows) * heads;
+
+  pdl_wait();
+  pdl_launch_dependents();
+  if (kFp8 && p.split_k_flag != nullptr) {
+    const long long n = static_cast<long long>(p.num_req) * p.hkv;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      p.split_k_flag[i] = 0;
+    }
+  }
+  if (warp_global >= items) return;
+  const int row = static_cast<int>(warp_global / heads);
+  const int head = static_cast<int>(warp_global % heads);
+
+  // request of this row: the last r with q_index[r] <= row (padding requests have empty ranges)
+  int lo = 0, hi = p.num_req;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(p.q_index + mid) <= row) {
+      lo = mid;
+    } else {
+      hi = mid - 1;
+    }
+  }
+  const int req = lo;
+  if (req >= p.num_req) return;
+  const int q0 = __ldg(p.q_index + req), q1 = __ldg(p.q_index + req + 1);
+  if (row < q0 || row >= q1) return;  // padding row
+  const int sl = __ldg(p.seqlen + req);
+  const int qlen = q1 - q0;
+  const int pos = sl - qlen + (row - q0);  // absolute position of this token
+  if (pos < 0) return;
+
+  const long long row_elems = static_cast<long long>(p.hq) * p.dqk + static_cast<long long>(p.hkv) * (p.dqk + p.dv);
+  const __nv_bfloat16* src = p.qkv + static_cast<long long>(row) * row_elems;
+  const bool is_q = head < p.hq;
+  const bool is_k = !is_q && head < p.hq + p.hkv;
+  const int kvh = is_q ? 0 : (is_k ? head - p.hq : head - p.hq - p.hkv);
+
+  // cache slot of this token
+  const int bi = pos / p.block_size, pb = pos - bi * p.block_size;
+  long long cb = 0;
+  if (!is_q) cb = __ldg(p.kv_indices + static_cast<long long>(req) * p.max_blocks + bi);
+
+  if (!is_q && !is_k) {
+    // ---------------- V: copy (bf16) or static quantisation (fp8) ----------------
+    const __nv_bfloat16* v = src + static_cast<long long>(p.hq + p.hkv) * p.dqk + static_cast<long long>(kvh) * p.dv;
+    OutT* dst = p.out_v != nullptr
+                    ? static_cast<OutT*>(p.out_v) + (static_cast<long long>(row) * p.hkv + kvh) * p.dv
+                    : static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride +
+                          (static_cast<long long>(pb) * p.hkv + kvh) * p.dv;
+    const float mult = kFp8 ? __frcp_rn(__ldg(p.v_scale)) : 1.f;
+    for (int d = 2 * lane; d < p.dv; d += 64) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + d));
+      store2<OutT>(dst + d, f.x * mult, f.y * mult);
+    }
+    if (p.out_v == nullptr && pos == sl - 1) {
+      // zero the unused tail of the request's last page (this kv head)
+      for (int s = pb + 1; s < p.block_size; s++) {
+        OutT* z = static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride +
+                  (static_cast<long long>(s) * p.hkv + kvh) * p.dv;
+        for (int d = 2 * lane; d < p.dv; d += 64) store2<OutT>(z + d, 0.f, 0.f);
+      }
+    }
+    return;
+  }
+
+  // ---------------- Q / K: RoPE (+ RMSNorm) ----------------
+  const int D = p.dqk, half = D / 2;
+  const __nv_bfloat16* x = src + (is_q ? static_cast<long long>(head) * D
+                                       : static_cast<long long>(p.hq) * D + static_cast<long long>(kvh) * D);
+  const float* cs = p.cos_sin + static_cast<long long>(pos) * D;
+  const float* nw = is_q ? p.q_norm_w : p.k_norm_w;
+  constexpr int kMaxChunks = 4;  // head dims up to 512
+  float a[kMaxChunks][2], b[kMaxChunks][2];  // lower-half / upper-half values of this lane
+  float ssq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; c++) {
+    const int d = c * 64 + 2 * lane;
+    if (d < half) {
+      const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + d));
+      const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + half + d));
+      a[c][0] = lo2.x; a[c][1] = lo2.y; b[c][0] = hi2.x; b[c][1] = hi2.y;
+      ssq += lo2.x * lo2.x + lo2.y * lo2.y + hi2.x * hi2.x + hi2.y * hi2.y;
+    }
+  }
+  auto rms = [&](float sum_sq) {
+    const float r = rsqrtf(warp_sum_f32(sum_sq) / static_cast<float>(D) + 1e-6f);
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++) {
+      const int d = c * 64 + 2 * lane;
+      if (d < half) {
+        a[c][0] *= r * __ldg(nw + d); a[c][1] *= r * __ldg(nw + d + 1);
+        b[c][0] *= r * __ldg(nw + half + d); b[c][1] *= r * __ldg(nw + half + d + 1);
+      }
+    }
+  };
+  if (p.norm_policy == 2) rms(ssq);
+  ssq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; c++) {
+    const int d = c * 64 + 2 * lane;
+    if (d < half) {
+      const float2 co = *reinterpret_cast<const float2*>(cs + d);
+      const float2 si = *reinterpret_cast<const float2*>(cs + half + d);
+      const float l0 = a[c][0] * co.x - b[c][0] * si.x, l1 = a[c][1] * co.y - b[c][1] * si.y;
+      const float h0 = b[c][0] * co.x + a[c][0] * si.x, h1 = b[c][1] * co.y + a[c][1] * si.y;
+      a[c][0] = l0; a[c][1] = l1; b[c][0] = h0; b[c][1] = h1;
+      ssq += l0 * l0 + l1 * l1 + h0 * h0 + h1 * h1;
+    }
+  }
+  if (p.norm_policy == 1) rms(ssq);
+
+  float mult = 1.f;
+  if (kFp8) {
+    if (is_q) {
+      if (p.quant_policy == 1) {
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxChunks; c++) {
+          if (c * 64 + 2 * lane < half) {
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(a[c][0]), fabsf(a[c][1])), fmaxf(fabsf(b[c][0]), fabsf(b[c][1]))));
+          }
+        }
+        m = warp_max_f32(m);
+        const float qs = m / p.upper_max;
+        if (lane == 0) {
+          if (p.is_prefill) {
+            p.q_scale[(static_cast<long long>(req) * p.hq + head) * p.max_seqlen_aligned + (row - q0)] = qs;
+          } else {
+            p.q_scale[static_cast<long long>(row) * p.hq + head] = qs;
+          }
+        }
+        mult = qs > 0.f ? __frcp_rn(qs) : 0.f;
+      } else {
+        mult = __ldg(p.q_scale_inv);
+      }
+    } else {
+      mult = __frcp_rn(__ldg(p.k_scale));
+    }
+  }
+  OutT* dst;
+  if (is_q) {
+    dst = static_cast<OutT*>(p.out_q) + (static_cast<long long>(row) * p.hq + head) * D;
+  } else if (p.out_k != nullptr) {
+    dst = static_cast<OutT*>(p.out_k) + (static_cast<long long>(row) * p.hkv + kvh) * D;
+  } else {
+    dst = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + (static_cast<long long>(pb) * p.hkv + kvh) * D;
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; c++) {
+    const int d = c * 64 + 2 * lane;
+    if (d < half) {
+      store2<OutT>(dst + d, a[c][0] * mult, a[c][1] * mult);
+      store2<OutT>(dst + half + d, b[c][0] * mult, b[c][1] * mult);
+    }
+  }
+  if (is_k && p.out_k == nullptr && pos == sl - 1) {
+    for (int s = pb + 1; s < p.block_size; s++) {
+      OutT* z = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + (static_cast<long long>(s) * p.hkv + kvh) * D;
+      for (int d = 2 * lane; d < D; d += 64) store2<OutT>(z + d, 0.f, 0.f);
+    }
+  }
+}
+
+static int launch(bool fp8, const Params& p, cudaStream_t stream) {
+  HPC_REQUIRE(p.dqk % 4 == 0 && p.dqk >= 4 && p.dqk <= 512 && p.dv % 2 == 0 && p.dv > 0,
+              "rope: head dims qk=%d v=%d unsupported (qk multiple of 4 up to 512, v even)", p.dqk, p.dv);
+  HPC_REQUIRE(p.block_size > 0 && p.hq > 0 && p.hkv > 0 && p.num_req > 0, "rope: bad geometry");
+  HPC_REQUIRE(p.norm_policy >= 0 && p.norm_policy <= 2, "rope: qk_norm_policy must be 0, 1 or 2");
+  if (p.norm_policy != 0) {
+    HPC_REQUIRE(p.q_norm_w != nullptr && p.k_norm_w != nullptr, "rope: norm weights required");
+  }
+  if (p.num_rows <= 0) return HPC_OK;
+  const long long items = static_cast<long long>(p.num_rows) * (p.hq + 2 * p.hkv);
+  const long long blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  HPC_REQUIRE(blocks < (1ll << 31), "rope: too many rows");
+  if (fp8) {
+    HPC_CUDA_CHECK(launch_pdl(rope_norm_store_kv_kernel<true>, dim3(static_cast<unsigned>(blocks)),
+                              dim3(kWarpsPerBlock * 32), 0, stream, 1, p));
+  } else {
+    HPC_CUDA_CHECK(launch_pdl(rope_norm_store_kv_kernel<false>, dim3(static_cast<unsigned>(blocks)),
+                              dim3(kWarpsPerBlock * 32), 0, stream, 1, p));
+  }
+  return HPC_OK;
+}
+
+}  // namespace rope
+}  // namespace b200
+
+using namespace b200;  // NOLINT
+
+// replaces reference src/rope/rope.h:15-25 (rope_norm_store_kv_async), same arguments
+extern "C" int hpc_rope_norm_store_kv_async(
+    void* out_q_ptr, void* kcache_ptr, void* vcache_ptr, void* out_k_ptr, void* out_v_ptr,
+    const void* in_qkv_ptr, const float* cos_sin_ptr, const int* num_seqlen_per_req_ptr,
+    const int* q_index_ptr, const int* kvcache_indices_ptr, const float* q_norm_weight_ptr,
+    const float* k_norm_weight_ptr, int kcache_block_offset, int vcache_block_offset, int num_batch,
+    int max_num_kv_block_per_batch, int kv_block_size, int num_rows, int num_q_heads,
+    int num_kv_heads, int qk_head_dim, int v_head_dim, int is_prefill, int qk_norm_policy,
+    cudaStream_t stream) {
+  rope::Params p{};
+  p.out_q = out_q_ptr; p.kcache = kcache_ptr; p.vcache = vcache_ptr; p.out_k = out_k_ptr; p.out_v = out_v_ptr;
+  p.qkv = static_cast<const __nv_bfloat16*>(in_qkv_ptr);
+  p.cos_sin = cos_sin_ptr; p.seqlen = num_seqlen_per_req_ptr; p.q_index = q_index_ptr;
+  p.kv_indices = kvcache_indices_ptr; p.q_norm_w = q_norm_weight_ptr; p.k_norm_w = k_norm_weight_ptr;
+  p.kcache_block_stride = kcache_block_offset; p.vcache_block_stride = vcache_block_offset;
+  p.num_req = num_batch; p.max_blocks = max_num_kv_block_per_batch; p.block_size = kv_block_size;
+  p.num_rows = num_rows; p.hq = num_q_heads; p.hkv = num_kv_heads; p.dqk = qk_head_dim; p.dv = v_head_dim;
+  p.is_prefill = is_prefill; p.norm_policy = qk_norm_policy; p.quant_policy = 0; p.upper_max = 448.f;
+  return rope::launch(false, p, stream);
+}
+
+// replaces reference src/rope/rope.h:27-38 (rope_norm_store_kv_fp8_async), same arguments
+extern "C" int hpc_rope_norm_store_kv_fp8_async(
+    void* out_q_ptr, void* kcache_ptr, void* vcache_ptr, void* out_k_ptr, void* out_v_ptr,
+    int32_t* split_k_flag_ptr, float* q_scale_ptr, const void* in_qkv_ptr, const float* cos_sin_ptr,
+    const int* num_seqlen_per_req_ptr, const int* q_index_ptr, const int* kvcache_indices_ptr,
+    const float* q_norm_weight_ptr, const float* k_norm_weight_ptr, const float* k_scale_ptr,
+    const float* v_scale_ptr, const float* q_scale_inv_ptr, float upper_max, int max_seqlens,
+    int kcache_block_offset, int vcache_block_offset, int num_batch, int max_num_kv_block_per_batch,
+    int kv_block_size, int num_rows, int num_q_heads, int num_kv_heads, int qk_head_dim,
+    int v_head_dim, int is_prefill, int qk_norm_policy, int quant_policy, cudaStream_t stream) {
+  HPC_REQUIRE(quant_policy == 1 || quant_policy == 2, "rope fp8: quant_policy must be 1 or 2");
+  HPC_REQUIRE(k_scale_ptr != nullptr && v_scale_ptr != nullptr, "rope fp8: k/v scales required");
+  HPC_REQUIRE(quant_policy == 1 ? q_scale_ptr != nullptr : q_scale_inv_ptr != nullptr,
+              "rope fp8: q_scale (policy 1) / q_scale_inv (policy 2) required");
+  HPC_REQUIRE(upper_max > 0.f && upper_max <= 448.f, "rope fp8: upper_max must be in (0, 448]");
+  rope::Params p{};
+  p.out_q = out_q_ptr; p.kcache = kcache_ptr; p.vcache = vcache_ptr; p.out_k = out_k_ptr; p.out_v = out_v_ptr;
+  p.split_k_flag = split_k_flag_ptr; p.q_scale = q_scale_ptr;
+  p.qkv = static_cast<const __nv_bfloat16*>(in_qkv_ptr);
+  p.cos_sin = cos_sin_ptr; p.seqlen = num_seqlen_per_req_ptr; p.q_index = q_index_ptr;
+  p.kv_indices = kvcache_indices_ptr; p.q_norm_w = q_norm_weight_ptr; p.k_norm_w = k_norm_weight_ptr;
+  p.k_scale = k_scale_ptr; p.v_scale = v_scale_ptr; p.q_scale_inv = q_scale_inv_ptr;
+  p.upper_max = upper_max; p.max_seqlen_aligned = (max_seqlens + 127) / 128 * 128;
+  p.kcache_block_stride = kcache_block_offset; p.vcache_block_stride = vcache_block_offset;
+  p.num_req = num_batch; p.max_blocks = max_num_kv_block_per_batch; p.block_size = kv_block_size;
+  p.num_rows = num_rows; p.hq = num_q_heads; p.hkv = num_kv_heads; p.dqk = qk_head_dim; p.dv = v_head_dim;
+  p.is_prefill = is_prefill; p.norm_policy = qk_norm_policy; p.quant_policy = quant_policy;
+  return rope::launch(true, p, stream);
+}

@@ -293,6 +293,31 @@ int hpc_selftest_umma_f8(const void* a_image, int a_bytes, const void* b_image, 
                          uint32_t a_sbo, uint32_t a_layout, uint32_t a_kstep, uint32_t b_lbo,
                          uint32_t b_sbo, uint32_t b_layout, uint32_t b_kstep, cudaStream_t stream);
 
+/* ---- RoPE + QK RMSNorm + paged KV-cache store (the producer of the cache layout attention reads) --
+ * replaces reference src/rope/rope.h:15-25 (rope_norm_store_kv_async) and :27-38
+ * (rope_norm_store_kv_fp8_async), argument for argument (bool -> int). Cache pages are
+ * [block_size, num_kv_heads, head_dim] contiguous, `*_block_offset` = elements between pages.
+ * fp8: k/v stored as x / scale (static per tensor); q dynamic per token-head (quant_policy 1, scale
+ * = amax / upper_max written to q_scale) or static (quant_policy 2, q * q_scale_inv[0]).
+ */
+int hpc_rope_norm_store_kv_async(
+    void* out_q_ptr, void* kcache_ptr, void* vcache_ptr, void* out_k_ptr, void* out_v_ptr,
+    const void* in_qkv_ptr, const float* cos_sin_ptr, const int* num_seqlen_per_req_ptr,
+    const int* q_index_ptr, const int* kvcache_indices_ptr, const float* q_norm_weight_ptr,
+    const float* k_norm_weight_ptr, int kcache_block_offset, int vcache_block_offset, int num_batch,
+    int max_num_kv_block_per_batch, int kv_block_size, int num_rows, int num_q_heads,
+    int num_kv_heads, int qk_head_dim, int v_head_dim, int is_prefill, int qk_norm_policy,
+    cudaStream_t stream);
+int hpc_rope_norm_store_kv_fp8_async(
+    void* out_q_ptr, void* kcache_ptr, void* vcache_ptr, void* out_k_ptr, void* out_v_ptr,
+    int32_t* split_k_flag_ptr, float* q_scale_ptr, const void* in_qkv_ptr, const float* cos_sin_ptr,
+    const int* num_seqlen_per_req_ptr, const int* q_index_ptr, const int* kvcache_indices_ptr,
+    const float* q_norm_weight_ptr, const float* k_norm_weight_ptr, const float* k_scale_ptr,
+    const float* v_scale_ptr, const float* q_scale_inv_ptr, float upper_max, int max_seqlens,
+    int kcache_block_offset, int vcache_block_offset, int num_batch, int max_num_kv_block_per_batch,
+    int kv_block_size, int num_rows, int num_q_heads, int num_kv_heads, int qk_head_dim,
+    int v_head_dim, int is_prefill, int qk_norm_policy, int quant_policy, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

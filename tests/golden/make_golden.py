@@ -82,6 +82,31 @@ def decode_fp8_kpt_case(tag, num_batch, kv_lens, hkv, hq, seed, layout):
     print("wrote kpt", tag, gt.shape)
 
 
+def _bf16_bits(t):
+    return t.to(torch.bfloat16).contiguous().view(torch.int16).numpy()
+
+
+def rope_case(tag, num_req, is_prefill, mtp, hq, hkv, policy, seed):
+    """reference tests/test_rope.py `rope_norm_ref` (with its helpers) on seeded CPU inputs
+    (16-token pages keep the fixture small; bf16 tensors are stored as their bit patterns)."""
+    from synth import rope as sr
+    ns = extract_many(REF / "tests/test_rope.py", {"apply_rms_norm_reference",
+                                                    "apply_rotary_pos_emb_neox_reference", "rope_norm_ref"})
+    d = sr.make_inputs(num_req, is_prefill, mtp, hq, hkv, 128, kv_block_size=16, max_num_kv_blocks=24,
+                       max_rope_position=128, seed=seed, len_range=(10, 60), pad_decode=False)
+    kc, vc = d["kcache"].clone(), d["vcache"].clone()
+    q = ns["rope_norm_ref"](kc, vc, d["qkv"], d["cos_sin"], d["num_seqlen"], d["q_index"],
+                            d["kv_indices"], d["q_norm_w"], d["k_norm_w"], policy)
+    np.savez_compressed(
+        OUT / f"rope_{tag}.npz", qkv=_bf16_bits(d["qkv"]), num_seqlen=d["num_seqlen"].numpy(),
+        q_index=d["q_index"].numpy(), kv_indices=d["kv_indices"].numpy(),
+        kcache_in=_bf16_bits(d["kcache"]), vcache_in=_bf16_bits(d["vcache"]),
+        q_norm_w=d["q_norm_w"].numpy(), k_norm_w=d["k_norm_w"].numpy(), cos_sin=d["cos_sin"].numpy(),
+        out_q=_bf16_bits(q), kcache_out=_bf16_bits(kc), vcache_out=_bf16_bits(vc),
+        meta=np.array([num_req, int(is_prefill), -1 if mtp is None else mtp, hq, hkv, policy]))
+    print("wrote rope", tag, q.shape)
+
+
 def decode_bf16_c1():
     """BASELINE config 0: test_attention_decode_bf16 bs=2 h=4 d=64 seq=128 on the torch CPU path."""
     fn = extract(REF / "tests/test_attention_decode_bf16.py", "ref_attn_with_paged_kvcache_func")
@@ -283,5 +308,7 @@ if __name__ == "__main__":
     decode_fp8_case("b5_hnd", 5, [1, 64, 65, 300, 515], 2, 16, 10086, "HND")
     decode_fp8_kpt_case("b3_nhd", 3, [70, 129, 200], 1, 8, 41, "NHD")
     decode_fp8_kpt_case("b4_hnd", 4, [1, 64, 65, 300], 2, 8, 10086, "HND")
+    rope_case("prefill_p2", 3, True, None, 4, 1, 2, 1)
+    rope_case("decode_p1", 5, False, 1, 8, 2, 1, 2)
     decode_bf16_c1()
     taskmap_cases()
