@@ -46,7 +46,6 @@ constexpr int kEpiBar = 2;
 constexpr int kTileQ = 4;
 constexpr int kXsSlots = kStages + 2;  // activation-scale ring (see the producer)
 constexpr int kMaxKB = 128;            // K blocks per tile whose weight scales are staged (K <= 16384)
-constexpr int kPrefetch = 6;           // L2 prefetch distance of the weight tiles, in K blocks
 
 struct Params {
   const int* seqlens;      // [G] rows per group
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         t.nvalid = __shfl_sync(0xffffffffu, t.nvalid, 0);
         t.scol0 = __shfl_sync(0xffffffffu, t.scol0, 0);
         const uint32_t qs = tq % kTileQ;
-        HPC_TIMED(w_tq, mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1));
+        HPC_TIMED(w_tq, mbar_wait_warp(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1));
         const int nb0 = kFused ? t.nt : t.nt * 2;
         int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
         if (nb1 >= nblk_per_group) nb1 = nb0;
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t s = it % kStages;
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
-          HPC_TIMED(w_empty, mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1));
+          HPC_TIMED(w_empty, mbar_wait_warp(&empty[s], ((it / kStages) & 1) ^ 1));
           if (elect_one()) {
             uint32_t extra = 0;
             if constexpr (kBlockwise) {
@@ -344,13 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1)
               tma_load_2d_hint(a_dst, &tmap_a, &full[s], kb * kBK, t.row0, pol_a);
               tma_load_3d(b_dst, &tmap_b, &full[s], kb * kBK, nrow0, t.g);
               tma_load_3d(b_dst + kBBytes / 2, &tmap_b, &full[s], kb * kBK, nrow1, t.g);
-              // Weight tiles stream from HBM (~2 us under load) but a stage is requested only
-              // ~3 K blocks (~2 us) before its MMA: pull the tiles kPrefetch K blocks ahead into L2
-              // so that the stage load itself is an L2 hit.
-              if (kb + kPrefetch < KB && !(p.debug & 16)) {
-                tma_prefetch_l2_3d(&tmap_b, (kb + kPrefetch) * kBK, nrow0, t.g);
-                tma_prefetch_l2_3d(&tmap_b, (kb + kPrefetch) * kBK, nrow1, t.g);
-              }
+              // (Tried: TMA L2 prefetch of the weight tiles 6 K blocks ahead -- 6 % slower at C3, the
+              // operands are not what the MMA warp waits for)
             }
           }
           if (++xsl == kXsSlots) xsl = 0;
@@ -391,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       while (true) {
         const uint32_t qs = tq % kTileQ;
-        HPC_TIMED(w_tqm, mbar_wait(&tq_full[qs], (tq / kTileQ) & 1));
+        HPC_TIMED(w_tqm, mbar_wait_warp(&tq_full[qs], (tq / kTileQ) & 1));
         const int tile = __shfl_sync(0xffffffffu, s_tileq[qs], 0);
         __syncwarp();
         if (lane == 0) mbar_arrive(&tq_empty[qs]);
@@ -402,8 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t s = it % kStages;
           const bool new_acc = kBlockwise || kb == 0;
           const uint32_t buf = acc_it & 1;
-          HPC_TIMED(w_full, mbar_wait(&full[s], (it / kStages) & 1));
-          if (new_acc) HPC_TIMED(w_pempty, mbar_wait(&part_empty[buf], ((acc_it >> 1) & 1) ^ 1));
+          HPC_TIMED(w_full, mbar_wait_warp(&full[s], (it / kStages) & 1));
+          if (new_acc) HPC_TIMED(w_pempty, mbar_wait_warp(&part_empty[buf], ((acc_it >> 1) & 1) ^ 1));
           tc_fence_after();
           const uint64_t ad = adesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
           const uint64_t bd = bdesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
