@@ -111,7 +111,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -120,13 +120,15 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -423,6 +425,9 @@ def main():
 
         def leg(name, fn):
             t0 = time.perf_counter()
+            smp = ClockSampler(local_rank) if rank == 0 else None  # clocks / throttle reasons of this leg
+            if smp:
+                smp.start()
             try:
                 r = fn()
                 if isinstance(r, dict):
@@ -430,6 +435,8 @@ def main():
                 extra[name] = r
             except Exception as ex:  # noqa: BLE001  (a failed leg is reported, not hidden)
                 extra[name] = {"error": repr(ex)[:400]}
+            if smp:
+                extra[name]["clocks"] = smp.stop()
 
         if world == 1:
             leg("moe_c3", lambda: bx.moe_c3(hpc, dev))

@@ -100,10 +100,13 @@ lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]
 )
-lib.hpc_rope_norm_store_kv_async.restype = c_int
-lib.hpc_rope_norm_store_kv_async.argtypes = [c_ptr] * 12 + [c_int] * 12 + [c_ptr]
-lib.hpc_rope_norm_store_kv_fp8_async.restype = c_int
-lib.hpc_rope_norm_store_kv_fp8_async.argtypes = [c_ptr] * 17 + [c_f32] + [c_int] * 14 + [c_ptr]
+# (hasattr: tools/r2_ab.sh swaps in libraries built from older commits for on-box A/B timing; a
+# library without these symbols still fails loudly -- at the first rope call)
+if hasattr(lib, "hpc_rope_norm_store_kv_async"):
+    lib.hpc_rope_norm_store_kv_async.restype = c_int
+    lib.hpc_rope_norm_store_kv_async.argtypes = [c_ptr] * 12 + [c_int] * 12 + [c_ptr]
+    lib.hpc_rope_norm_store_kv_fp8_async.restype = c_int
+    lib.hpc_rope_norm_store_kv_fp8_async.argtypes = [c_ptr] * 17 + [c_f32] + [c_int] * 14 + [c_ptr]
 
 lib.hpc_selftest_umma_rate.restype = c_int
 lib.hpc_selftest_umma_rate.argtypes = [c_int] * 4 + [c_ptr, c_ptr]

@@ -49,7 +49,9 @@ def _common_checks(qkv, cos_sin, num_seqlen_per_req, q_index, kvcache_indices, q
 
 
 def _rope_impl(kcache, vcache, qkv, cos_sin, num_seqlen_per_req, q_index, kvcache_indices,
-               is_prefill, q_norm_weight, k_norm_weight, out_q, out_k, out_v, qk_norm_policy):
+               is_prefill, q_norm_weight=None, k_norm_weight=None, out_q=None, out_k=None, out_v=None,
+               qk_norm_policy=0):
+    # (trailing arguments equal to their schema defaults are not passed to a Python kernel)
     # reference src/rope/entry.cc:16-92
     _common_checks(qkv, cos_sin, num_seqlen_per_req, q_index, kvcache_indices, qk_norm_policy,
                    q_norm_weight, k_norm_weight)
@@ -138,7 +140,8 @@ def rope_norm_store_kv(
 
 @torch.library.register_fake("hpc::rope_norm_store_kv")
 def _rope_fake(kcache, vcache, qkv, cos_sin, num_seqlen_per_req, q_index, kvcache_indices, is_prefill,
-               q_norm_weight, k_norm_weight, out_q, out_k, out_v, qk_norm_policy):
+               q_norm_weight=None, k_norm_weight=None, out_q=None, out_k=None, out_v=None,
+               qk_norm_policy=0):
     hkv, dqk, dv = kcache.shape[-2], kcache.shape[-1], vcache.shape[-1]
     hq = (qkv.shape[-1] - hkv * dqk - hkv * dv) // dqk
     return torch.empty(qkv.shape[0], hq, dqk, dtype=qkv.dtype, device=qkv.device)
