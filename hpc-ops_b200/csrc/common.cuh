@@ -179,13 +179,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Whole-warp roles (warp-uniform producer / issuer loops): one lane polls, the others park at the
-// warp barrier. 32 lanes spinning on try_wait would send 32x the requests through the shared-memory
-// pipe that the softmax / epilogue warps of the same SM partition are using.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
+// Whole-warp roles (warp-uniform producer / issuer loops) poll with ALL lanes. Polling with one lane
+// and parking the others at __syncwarp() was measured 1.6x slower on the grouped GEMM and the
+// prefill (on-box A/B, profiles/r2_ab_polling.txt): the divergent spin loop costs the uniformity the
+// whole-warp structure exists for.
 
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — tile mode loads, completion on an mbarrier

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       t.num_tile_kv = __shfl_sync(0xffffffffu, t.num_tile_kv, 0);
       {
         const int qb = qcnt & 1;
-        mbar_wait_warp(&q_empty[qb], ((qcnt >> 1) & 1) ^ 1);
+        mbar_wait(&q_empty[qb], ((qcnt >> 1) & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&q_full[qb], p.num_seq_q * p.group * kD);
           tma_load_3d(q_smem + qb * 4096, &tmap_q, &q_full[qb], 0, t.ihead_kv * p.group,
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int id0 = __shfl_sync(0xffffffffu, my_id, 2 * tt);
           const int id1 = __shfl_sync(0xffffffffu, my_id, 2 * tt + 1);
           const uint32_t st = n % kNumStages;
-          mbar_wait_warp(&stage_empty[st], ((n / kNumStages) & 1) ^ 1);
+          mbar_wait(&stage_empty[st], ((n / kNumStages) & 1) ^ 1);
           if (elect_one()) {
             uint8_t* dst = stages + st * kStageBytes;
             mbar_arrive_expect_tx(&k_full[st], kSlotBytes);
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto issue_pv = [&](uint32_t m) {
         const uint32_t st = m % kNumStages;
         const uint32_t buf = m & 1;
-        mbar_wait_warp(&p_full[buf], (m >> 1) & 1);
-        mbar_wait_warp(&v_full[st], (m / kNumStages) & 1);
+        mbar_wait(&p_full[buf], (m >> 1) & 1);
+        mbar_wait(&v_full[st], (m / kNumStages) & 1);
         tc_fence_after();
         const uint64_t ad = vdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
         const uint64_t bd = pdesc0 + static_cast<uint64_t>(buf * (L::kPBytes >> 4));
@@ -286,13 +286,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       Task t;
       for (const int* row = bin; load_task(row, t); row += kTaskStride) {
         const int qb = qcnt & 1;
-        mbar_wait_warp(&q_full[qb], (qcnt >> 1) & 1);
+        mbar_wait(&q_full[qb], (qcnt >> 1) & 1);
         const uint64_t bd = qdesc0 + static_cast<uint64_t>(qb * (4096 >> 4));
         const int ntiles = __shfl_sync(0xffffffffu, t.num_tile_kv, 0);
         for (int tt = 0; tt < ntiles; tt++) {
           const uint32_t st = n % kNumStages;
           const uint32_t buf = n & 1;
-          mbar_wait_warp(&k_full[st], (n / kNumStages) & 1);
+          mbar_wait(&k_full[st], (n / kNumStages) & 1);
           tc_fence_after();
           const uint64_t ad = kdesc0 + static_cast<uint64_t>(st * (kStageBytes >> 4));
           const uint32_t d = tmem_base + buf * NQ;

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         t.nvalid = __shfl_sync(0xffffffffu, t.nvalid, 0);
         t.scol0 = __shfl_sync(0xffffffffu, t.scol0, 0);
         const uint32_t qs = tq % kTileQ;
-        HPC_TIMED(w_tq, mbar_wait_warp(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1));
+        HPC_TIMED(w_tq, mbar_wait(&tq_empty[qs], ((tq / kTileQ) & 1) ^ 1));
         const int nb0 = kFused ? t.nt : t.nt * 2;
         int nb1 = kFused ? nblk_per_group / 2 + t.nt : t.nt * 2 + 1;
         if (nb1 >= nblk_per_group) nb1 = nb0;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t s = it % kStages;
           uint8_t* a_dst = stages + s * kStageBytes;
           uint8_t* b_dst = a_dst + kABytes;
-          HPC_TIMED(w_empty, mbar_wait_warp(&empty[s], ((it / kStages) & 1) ^ 1));
+          HPC_TIMED(w_empty, mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1));
           if (elect_one()) {
             uint32_t extra = 0;
             if constexpr (kBlockwise) {
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       while (true) {
         const uint32_t qs = tq % kTileQ;
-        HPC_TIMED(w_tqm, mbar_wait_warp(&tq_full[qs], (tq / kTileQ) & 1));
+        HPC_TIMED(w_tqm, mbar_wait(&tq_full[qs], (tq / kTileQ) & 1));
         const int tile = __shfl_sync(0xffffffffu, s_tileq[qs], 0);
         __syncwarp();
         if (lane == 0) mbar_arrive(&tq_empty[qs]);
@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t s = it % kStages;
           const bool new_acc = kBlockwise || kb == 0;
           const uint32_t buf = acc_it & 1;
-          HPC_TIMED(w_full, mbar_wait_warp(&full[s], (it / kStages) & 1));
-          if (new_acc) HPC_TIMED(w_pempty, mbar_wait_warp(&part_empty[buf], ((acc_it >> 1) & 1) ^ 1));
+          HPC_TIMED(w_full, mbar_wait(&full[s], (it / kStages) & 1));
+          if (new_acc) HPC_TIMED(w_pempty, mbar_wait(&part_empty[buf], ((acc_it >> 1) & 1) ^ 1));
           tc_fence_after();
           const uint64_t ad = adesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));
           const uint64_t bd = bdesc0 + static_cast<uint64_t>(s * (kStageBytes >> 4));

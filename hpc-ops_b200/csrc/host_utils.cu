@@ -42,31 +42,6 @@ int device_slot() {
   return dev < 64 ? dev : 63;
 }
 
-int* launch_counter(cudaStream_t stream) {
-  constexpr int kPool = 256;
-  static int* pool[64] = {nullptr};
-  static unsigned next[64] = {0};
-  static std::mutex mu;
-  const int dev = device_slot();
-  int* slot = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (pool[dev] == nullptr) {
-      if (cudaMalloc(&pool[dev], kPool * sizeof(int)) != cudaSuccess) {
-        set_last_error("launch_counter: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
-        pool[dev] = nullptr;
-        return nullptr;
-      }
-    }
-    slot = pool[dev] + (next[dev]++ % kPool);
-  }
-  if (cudaMemsetAsync(slot, 0, sizeof(int), stream) != cudaSuccess) {
-    set_last_error("launch_counter: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return nullptr;
-  }
-  return slot;
-}
-
 int* scheduler_counter(cudaStream_t stream) {
   constexpr int kSlots = 128;
   struct Entry {

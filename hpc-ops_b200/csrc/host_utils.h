@@ -38,10 +38,6 @@ bool pdl_enabled();
 // Current CUDA device clamped to [0, 63] (0 when the runtime is unavailable). Launchers keep their
 // one-time state (function attributes, scratch pools) per device: one process may drive several GPUs.
 int device_slot();
-// A zeroed int32 in device memory for one launch (dynamic tile / work counters): taken from a
-// rotating per-device pool of 256 and cleared with cudaMemsetAsync on `stream`. The pool is
-// allocated on the first call per device, which therefore must not happen inside a stream capture.
-int* launch_counter(cudaStream_t stream);
 // Two zeroed int32 (work counter, finished-CTA counter) owned by `stream` for kernels that re-arm
 // their scheduler themselves (the last CTA resets both): no memset between launches, so PDL chains
 // and graph replays are unaffected. One slot per (device, stream), allocated and zeroed on first

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         Work k;
         const bool alive = decode_work(p, w, k);
         if (alive && k.rows == 0) continue;  // Q tile beyond this request
-        mbar_wait_warp(q_empty, (item & 1) ^ 1);
+        mbar_wait(q_empty, (item & 1) ^ 1);
         int nact = 0;
         if (alive) {
           // ---- active tile list (ballot compaction, ascending j) ----
@@ -178,7 +178,19 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
         __syncwarp();
         item++;
-        if (!alive) break;
+        if (!alive) {
+          // the last CTA out re-arms the work counter for the next launch (no memset node between
+          // launches; one counter pair per stream, see host_utils.h scheduler_counter)
+          if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(p.work_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+              p.work_counter[0] = 0;
+              p.work_counter[1] = 0;
+              __threadfence();
+            }
+          }
+          break;
+        }
         // ---- K/V tiles of the active list ----
         const int hkv = u_hq / p.group;
         const int nblk = (k.seq_kv + kPage - 1) / kPage;
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             const int id1 = __shfl_sync(0xffffffffu, id, 2 * t + 1);
             const uint32_t st = n % kStages;
             const uint32_t ph = ((n / kStages) & 1) ^ 1;
-            mbar_wait_warp(&k_empty[st], ph);  // QK(n - 2) finished
+            mbar_wait(&k_empty[st], ph);  // QK(n - 2) finished
             if (elect_one()) {
               uint8_t* kd8 = k_smem + st * kTileBytes;
               mbar_arrive_expect_tx(&k_full[st], kTileBytes + (kKPerToken ? 512 : 0));
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 2)
               }
             }
             __syncwarp();
-            mbar_wait_warp(&v_empty[st], ph);  // PV(n - 2) finished
+            mbar_wait(&v_empty[st], ph);  // PV(n - 2) finished
             if (elect_one()) {
               uint8_t* vd8 = v_smem + st * kTileBytes;
               mbar_arrive_expect_tx(&v_full[st], kTileBytes);
@@ -242,8 +254,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       // S(m) = Q . K(m)^T; needs K(m) in smem and S(m-1) drained into the softmax registers
       auto issue_qk = [&](const uint32_t m, const bool last_of_item) {
         const uint32_t st = m % kStages;
-        mbar_wait_warp(&k_full[st], (m / kStages) & 1);
-        if (m > 0) mbar_wait_warp(s_free, (m - 1) & 1);
+        mbar_wait(&k_full[st], (m / kStages) & 1);
+        if (m > 0) mbar_wait(s_free, (m - 1) & 1);
         tc_fence_after();
         const uint64_t kd = kdesc0 + static_cast<uint64_t>(st * (kTileBytes >> 4));
         if (elect_one()) {
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       uint32_t n = 0;
       uint32_t item = 0;
       while (true) {
-        mbar_wait_warp(q_full, item & 1);
+        mbar_wait(q_full, item & 1);
         const int w = __shfl_sync(0xffffffffu, s_work[0], 0);
         const int nact = __shfl_sync(0xffffffffu, s_work[1], 0);
         if (w < 0) break;
@@ -270,8 +282,8 @@ __global__ void __launch_bounds__(kThreads, 2)
           for (int i = 0; i < nact; i++) {
             if (i + 1 < nact) issue_qk(n + 1, i + 2 == nact);  // runs under softmax(n)
             const uint32_t st = n % kStages;
-            mbar_wait_warp(&v_full[st], (n / kStages) & 1);
-            mbar_wait_warp(p_full, n & 1);
+            mbar_wait(&v_full[st], (n / kStages) & 1);
+            mbar_wait(p_full, n & 1);
             tc_fence_after();
             const uint64_t vd = vdesc0 + static_cast<uint64_t>(st * (kTileBytes >> 4));
             if (elect_one()) {
@@ -571,7 +583,7 @@ static int prefill_launch(bool k_per_token, void* y_ptr, const void* q_ptr, cons
   rc = encode_cache_map(&tv, vcache_ptr, num_head_kv, num_kvcache_blocks, v_blk, v_tok, v_head, &vhf);
   if (rc) return rc;
 
-  int* counter = launch_counter(stream);  // work-item counter of this launch
+  int* counter = scheduler_counter(stream);  // work-item counter {next item, CTAs done}, self-resetting
   if (counter == nullptr) return HPC_ERR_CUDA;
 
   prefill::Params p;

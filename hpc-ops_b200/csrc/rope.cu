@@ -3,12 +3,12 @@
 // B200 build written from scratch; semantics of reference src/rope/rope.cu:99-418 (bf16) and
 // :420-850 (fp8), launcher contract of src/rope/rope.h:15-38.
 //
-// HBM-bound streaming kernel: one warp per (token row, head) item, where the heads of a row are
-// [q heads | k heads | v heads] exactly as they lie in the packed qkv row. A lane owns dims
-// {2l, 2l+1} of the lower half and the matching dims of the upper half (the NeoX rotation pairs),
-// i.e. 4-byte coalesced accesses (128 B per warp per half), fp32 math, warp-shuffle reductions for
-// the RMS and the dynamic Q amax. The warp of a request's LAST token also zeroes the unused tail
-// of that request's last cache page (the "unused slots are zero" contract of the attention ops).
+// HBM-bound streaming kernel: a warp handles (token row, group of 4 q or k heads | the row's whole V
+// segment). A lane owns dims {2l, 2l+1} of the lower half and the matching dims of the upper half
+// (the NeoX rotation pairs): 4-byte coalesced accesses (128 B per warp per half), 8 of them in
+// flight per lane; V is a contiguous 16-byte-vector copy / quantisation. fp32 math, warp-shuffle
+// reductions for the RMS and the dynamic Q amax. The warps of a request's LAST token also zero the
+// unused tail of that request's last cache page (the "unused slots are zero" contract of attention).
 #include "common.cuh"
 #include "host_utils.h"
 
@@ -53,15 +53,20 @@ __device__ __forceinline__ void store2<uint8_t>(uint8_t* dst, float a, float b) 
   *reinterpret_cast<uint16_t*>(dst) = cvt_e4m3x2(a, b);
 }
 
-// kFp8: caches / out_q are e4m3 (uint8_t), else bf16. kHalf = Dqk / 2 handled in chunks of 64 dims.
-template <bool kFp8>
+// Work unit of a warp: (token row, unit), units of a row = [groups of kU q heads | groups of kU k heads
+// | the whole V segment]. kCH = 64-dim chunks per rotation half (head dim <= 128 * kCH), kU = 4 / kCH
+// heads per unit, so that a lane has 8 independent 4-byte loads in flight per unit (a warp per single
+// head keeps only 2: measured 0.21 of HBM).
+template <bool kFp8, int kCH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     rope_norm_store_kv_kernel(const Params p) {
   using OutT = typename std::conditional<kFp8, uint8_t, __nv_bfloat16>::type;
+  constexpr int kU = 4 / kCH;
   const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int heads = p.hq + 2 * p.hkv;
-  const long long items = static_cast<long long>(p.num_rows) * heads;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int qg = (p.hq + kU - 1) / kU, kg = (p.hkv + kU - 1) / kU;
+  const int units = qg + kg + 1;
+  const long long items = static_cast<long long>(p.num_rows) * units;
 
   pdl_wait();
   pdl_launch_dependents();
@@ -73,8 +78,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
   }
   if (warp_global >= items) return;
-  const int row = static_cast<int>(warp_global / heads);
-  const int head = static_cast<int>(warp_global % heads);
+  const int row = static_cast<int>(warp_global / units);
+  const int unit = static_cast<int>(warp_global % units);
 
   // request of this row: the last r with q_index[r] <= row (padding requests have empty ranges)
   int lo = 0, hi = p.num_req;
@@ -91,100 +96,136 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   const int q0 = __ldg(p.q_index + req), q1 = __ldg(p.q_index + req + 1);
   if (row < q0 || row >= q1) return;  // padding row
   const int sl = __ldg(p.seqlen + req);
-  const int qlen = q1 - q0;
-  const int pos = sl - qlen + (row - q0);  // absolute position of this token
+  const int pos = sl - (q1 - q0) + (row - q0);  // absolute position of this token
   if (pos < 0) return;
 
   const long long row_elems = static_cast<long long>(p.hq) * p.dqk + static_cast<long long>(p.hkv) * (p.dqk + p.dv);
   const __nv_bfloat16* src = p.qkv + static_cast<long long>(row) * row_elems;
-  const bool is_q = head < p.hq;
-  const bool is_k = !is_q && head < p.hq + p.hkv;
-  const int kvh = is_q ? 0 : (is_k ? head - p.hq : head - p.hq - p.hkv);
+  const bool is_q = unit < qg;
+  const bool is_k = !is_q && unit < qg + kg;
 
   // cache slot of this token
   const int bi = pos / p.block_size, pb = pos - bi * p.block_size;
   long long cb = 0;
   if (!is_q) cb = __ldg(p.kv_indices + static_cast<long long>(req) * p.max_blocks + bi);
+  const bool last_tok = pos == sl - 1;
 
   if (!is_q && !is_k) {
-    // ---------------- V: copy (bf16) or static quantisation (fp8) ----------------
-    const __nv_bfloat16* v = src + static_cast<long long>(p.hq + p.hkv) * p.dqk + static_cast<long long>(kvh) * p.dv;
+    // ---------------- V: all kv heads of the token are contiguous in the row and in the page ------
+    const int n = p.hkv * p.dv;  // elements
+    const __nv_bfloat16* v = src + static_cast<long long>(p.hq + p.hkv) * p.dqk;
     OutT* dst = p.out_v != nullptr
-                    ? static_cast<OutT*>(p.out_v) + (static_cast<long long>(row) * p.hkv + kvh) * p.dv
-                    : static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride +
-                          (static_cast<long long>(pb) * p.hkv + kvh) * p.dv;
+                    ? static_cast<OutT*>(p.out_v) + static_cast<long long>(row) * n
+                    : static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride + static_cast<long long>(pb) * n;
     const float mult = kFp8 ? __frcp_rn(__ldg(p.v_scale)) : 1.f;
-    for (int d = 2 * lane; d < p.dv; d += 64) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + d));
-      store2<OutT>(dst + d, f.x * mult, f.y * mult);
-    }
-    if (p.out_v == nullptr && pos == sl - 1) {
-      // zero the unused tail of the request's last page (this kv head)
-      for (int s = pb + 1; s < p.block_size; s++) {
-        OutT* z = static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride +
-                  (static_cast<long long>(s) * p.hkv + kvh) * p.dv;
-        for (int d = 2 * lane; d < p.dv; d += 64) store2<OutT>(z + d, 0.f, 0.f);
+    if ((n & 7) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dst) & (kFp8 ? 7 : 15)) == 0) {
+      for (int e = lane * 8; e < n; e += 256) {
+        const uint4 raw = ld_nc_v4(v + e);
+        if constexpr (kFp8) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+          const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+          uint2 o;
+          o.x = cvt_e4m3x4(f0.x * mult, f0.y * mult, f1.x * mult, f1.y * mult);
+          o.y = cvt_e4m3x4(f2.x * mult, f2.y * mult, f3.x * mult, f3.y * mult);
+          *reinterpret_cast<uint2*>(dst + e) = o;
+        } else {
+          *reinterpret_cast<uint4*>(dst + e) = raw;
+        }
       }
+    } else {
+      for (int e = 2 * lane; e < n; e += 64) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + e));
+        store2<OutT>(dst + e, f.x * mult, f.y * mult);
+      }
+    }
+    if (p.out_v == nullptr && last_tok) {
+      // zero the unused tail of the request's last page: contiguous (block_size - pb - 1) * n elements
+      OutT* z = static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride + static_cast<long long>(pb + 1) * n;
+      const long long cnt = static_cast<long long>(p.block_size - pb - 1) * n;
+      for (long long e = 2 * lane; e < cnt; e += 64) store2<OutT>(z + e, 0.f, 0.f);
     }
     return;
   }
 
-  // ---------------- Q / K: RoPE (+ RMSNorm) ----------------
+  // ---------------- Q / K: RoPE (+ RMSNorm) on up to kU heads, loads first ----------------
   const int D = p.dqk, half = D / 2;
-  const __nv_bfloat16* x = src + (is_q ? static_cast<long long>(head) * D
-                                       : static_cast<long long>(p.hq) * D + static_cast<long long>(kvh) * D);
+  const int nheads = is_q ? p.hq : p.hkv;
+  const int h0 = (is_q ? unit : unit - qg) * kU;
+  const __nv_bfloat16* xbase = src + (is_q ? 0ll : static_cast<long long>(p.hq) * D);
   const float* cs = p.cos_sin + static_cast<long long>(pos) * D;
   const float* nw = is_q ? p.q_norm_w : p.k_norm_w;
-  constexpr int kMaxChunks = 4;  // head dims up to 512
-  float a[kMaxChunks][2], b[kMaxChunks][2];  // lower-half / upper-half values of this lane
-  float ssq = 0.f;
+
+  float a[kU][kCH][2], b[kU][kCH][2];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; c++) {
-    const int d = c * 64 + 2 * lane;
-    if (d < half) {
-      const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + d));
-      const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + half + d));
-      a[c][0] = lo2.x; a[c][1] = lo2.y; b[c][0] = hi2.x; b[c][1] = hi2.y;
-      ssq += lo2.x * lo2.x + lo2.y * lo2.y + hi2.x * hi2.x + hi2.y * hi2.y;
-    }
-  }
-  auto rms = [&](float sum_sq) {
-    const float r = rsqrtf(warp_sum_f32(sum_sq) / static_cast<float>(D) + 1e-6f);
+  for (int u = 0; u < kU; u++) {
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; c++) {
+    for (int c = 0; c < kCH; c++) {
       const int d = c * 64 + 2 * lane;
-      if (d < half) {
-        a[c][0] *= r * __ldg(nw + d); a[c][1] *= r * __ldg(nw + d + 1);
-        b[c][0] *= r * __ldg(nw + half + d); b[c][1] *= r * __ldg(nw + half + d + 1);
+      if (h0 + u < nheads && d < half) {
+        const __nv_bfloat16* x = xbase + static_cast<long long>(h0 + u) * D;
+        const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + d));
+        const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + half + d));
+        a[u][c][0] = lo2.x; a[u][c][1] = lo2.y; b[u][c][0] = hi2.x; b[u][c][1] = hi2.y;
+      } else {
+        a[u][c][0] = a[u][c][1] = b[u][c][0] = b[u][c][1] = 0.f;
       }
     }
-  };
-  if (p.norm_policy == 2) rms(ssq);
-  ssq = 0.f;
+  }
+  float2 co[kCH], si[kCH];
+  float wl[kCH][2], wh[kCH][2];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; c++) {
+  for (int c = 0; c < kCH; c++) {
     const int d = c * 64 + 2 * lane;
     if (d < half) {
-      const float2 co = *reinterpret_cast<const float2*>(cs + d);
-      const float2 si = *reinterpret_cast<const float2*>(cs + half + d);
-      const float l0 = a[c][0] * co.x - b[c][0] * si.x, l1 = a[c][1] * co.y - b[c][1] * si.y;
-      const float h0 = b[c][0] * co.x + a[c][0] * si.x, h1 = b[c][1] * co.y + a[c][1] * si.y;
-      a[c][0] = l0; a[c][1] = l1; b[c][0] = h0; b[c][1] = h1;
-      ssq += l0 * l0 + l1 * l1 + h0 * h0 + h1 * h1;
+      co[c] = *reinterpret_cast<const float2*>(cs + d);
+      si[c] = *reinterpret_cast<const float2*>(cs + half + d);
+      if (p.norm_policy != 0) {
+        wl[c][0] = __ldg(nw + d); wl[c][1] = __ldg(nw + d + 1);
+        wh[c][0] = __ldg(nw + half + d); wh[c][1] = __ldg(nw + half + d + 1);
+      }
+    } else {
+      co[c] = si[c] = make_float2(0.f, 0.f);
     }
   }
-  if (p.norm_policy == 1) rms(ssq);
+  const float k_mult = (kFp8 && !is_q) ? __frcp_rn(__ldg(p.k_scale)) : 1.f;
 
-  float mult = 1.f;
-  if (kFp8) {
-    if (is_q) {
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    if (h0 + u >= nheads) break;  // warp-uniform
+    const int head = h0 + u;
+    auto rms = [&]() {
+      float ssq = 0.f;
+#pragma unroll
+      for (int c = 0; c < kCH; c++) {
+        ssq += a[u][c][0] * a[u][c][0] + a[u][c][1] * a[u][c][1] + b[u][c][0] * b[u][c][0] + b[u][c][1] * b[u][c][1];
+      }
+      const float r = rsqrtf(warp_sum_f32(ssq) / static_cast<float>(D) + 1e-6f);
+#pragma unroll
+      for (int c = 0; c < kCH; c++) {
+        if (c * 64 + 2 * lane < half) {
+          a[u][c][0] *= r * wl[c][0]; a[u][c][1] *= r * wl[c][1];
+          b[u][c][0] *= r * wh[c][0]; b[u][c][1] *= r * wh[c][1];
+        }
+      }
+    };
+    if (p.norm_policy == 2) rms();
+#pragma unroll
+    for (int c = 0; c < kCH; c++) {
+      const float l0 = a[u][c][0] * co[c].x - b[u][c][0] * si[c].x, l1 = a[u][c][1] * co[c].y - b[u][c][1] * si[c].y;
+      const float g0 = b[u][c][0] * co[c].x + a[u][c][0] * si[c].x, g1 = b[u][c][1] * co[c].y + a[u][c][1] * si[c].y;
+      a[u][c][0] = l0; a[u][c][1] = l1; b[u][c][0] = g0; b[u][c][1] = g1;
+    }
+    if (p.norm_policy == 1) rms();
+
+    float mult = k_mult;
+    if (kFp8 && is_q) {
       if (p.quant_policy == 1) {
         float m = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxChunks; c++) {
-          if (c * 64 + 2 * lane < half) {
-            m = fmaxf(m, fmaxf(fmaxf(fabsf(a[c][0]), fabsf(a[c][1])), fmaxf(fabsf(b[c][0]), fabsf(b[c][1]))));
-          }
+        for (int c = 0; c < kCH; c++) {
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(a[u][c][0]), fabsf(a[u][c][1])), fmaxf(fabsf(b[u][c][0]), fabsf(b[u][c][1]))));
         }
         m = warp_max_f32(m);
         const float qs = m / p.upper_max;
@@ -199,32 +240,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
       } else {
         mult = __ldg(p.q_scale_inv);
       }
+    }
+    OutT* dst;
+    if (is_q) {
+      dst = static_cast<OutT*>(p.out_q) + (static_cast<long long>(row) * p.hq + head) * D;
+    } else if (p.out_k != nullptr) {
+      dst = static_cast<OutT*>(p.out_k) + (static_cast<long long>(row) * p.hkv + head) * D;
     } else {
-      mult = __frcp_rn(__ldg(p.k_scale));
+      dst = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + (static_cast<long long>(pb) * p.hkv + head) * D;
     }
-  }
-  OutT* dst;
-  if (is_q) {
-    dst = static_cast<OutT*>(p.out_q) + (static_cast<long long>(row) * p.hq + head) * D;
-  } else if (p.out_k != nullptr) {
-    dst = static_cast<OutT*>(p.out_k) + (static_cast<long long>(row) * p.hkv + kvh) * D;
-  } else {
-    dst = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + (static_cast<long long>(pb) * p.hkv + kvh) * D;
-  }
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; c++) {
-    const int d = c * 64 + 2 * lane;
-    if (d < half) {
-      store2<OutT>(dst + d, a[c][0] * mult, a[c][1] * mult);
-      store2<OutT>(dst + half + d, b[c][0] * mult, b[c][1] * mult);
+    for (int c = 0; c < kCH; c++) {
+      const int d = c * 64 + 2 * lane;
+      if (d < half) {
+        store2<OutT>(dst + d, a[u][c][0] * mult, a[u][c][1] * mult);
+        store2<OutT>(dst + half + d, b[u][c][0] * mult, b[u][c][1] * mult);
+      }
     }
   }
-  if (is_k && p.out_k == nullptr && pos == sl - 1) {
-    for (int s = pb + 1; s < p.block_size; s++) {
-      OutT* z = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + (static_cast<long long>(s) * p.hkv + kvh) * D;
-      for (int d = 2 * lane; d < D; d += 64) store2<OutT>(z + d, 0.f, 0.f);
-    }
+  if (is_k && unit == qg && p.out_k == nullptr && last_tok) {
+    // K tail of the request's last page, all kv heads: contiguous
+    const int n = p.hkv * D;
+    OutT* z = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + static_cast<long long>(pb + 1) * n;
+    const long long cnt = static_cast<long long>(p.block_size - pb - 1) * n;
+    for (long long e = 2 * lane; e < cnt; e += 64) store2<OutT>(z + e, 0.f, 0.f);
   }
+}
+
+template <bool kFp8, int kCH>
+static int launch_impl(const Params& p, cudaStream_t stream) {
+  constexpr int kU = 4 / kCH;
+  const long long units = (p.hq + kU - 1) / kU + (p.hkv + kU - 1) / kU + 1;
+  const long long items = static_cast<long long>(p.num_rows) * units;
+  const long long blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  HPC_REQUIRE(blocks < (1ll << 31), "rope: too many rows");
+  HPC_CUDA_CHECK(launch_pdl(rope_norm_store_kv_kernel<kFp8, kCH>, dim3(static_cast<unsigned>(blocks)),
+                            dim3(kWarpsPerBlock * 32), 0, stream, 1, p));
+  return HPC_OK;
 }
 
 static int launch(bool fp8, const Params& p, cudaStream_t stream) {
@@ -236,17 +288,15 @@ static int launch(bool fp8, const Params& p, cudaStream_t stream) {
     HPC_REQUIRE(p.q_norm_w != nullptr && p.k_norm_w != nullptr, "rope: norm weights required");
   }
   if (p.num_rows <= 0) return HPC_OK;
-  const long long items = static_cast<long long>(p.num_rows) * (p.hq + 2 * p.hkv);
-  const long long blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  HPC_REQUIRE(blocks < (1ll << 31), "rope: too many rows");
+  const int ch = (p.dqk / 2 + 63) / 64;  // 64-dim chunks per rotation half
   if (fp8) {
-    HPC_CUDA_CHECK(launch_pdl(rope_norm_store_kv_kernel<true>, dim3(static_cast<unsigned>(blocks)),
-                              dim3(kWarpsPerBlock * 32), 0, stream, 1, p));
-  } else {
-    HPC_CUDA_CHECK(launch_pdl(rope_norm_store_kv_kernel<false>, dim3(static_cast<unsigned>(blocks)),
-                              dim3(kWarpsPerBlock * 32), 0, stream, 1, p));
+    if (ch <= 1) return launch_impl<true, 1>(p, stream);
+    if (ch <= 2) return launch_impl<true, 2>(p, stream);
+    return launch_impl<true, 4>(p, stream);
   }
-  return HPC_OK;
+  if (ch <= 1) return launch_impl<false, 1>(p, stream);
+  if (ch <= 2) return launch_impl<false, 2>(p, stream);
+  return launch_impl<false, 4>(p, stream);
 }
 
 }  // namespace rope

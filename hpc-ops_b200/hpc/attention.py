@@ -35,6 +35,9 @@ _TASK_BYTES = 48
 _TASK_INTS = 12
 
 
+_WORKSPACE_TEMPLATES = {}  # (device, geometry) -> zeroed task-map workspace with its header written
+
+
 def _num_total_ctas(device=None) -> int:
     return _ffi.sm_count(device) * _CTA_PER_SM
 
@@ -121,7 +124,7 @@ def _decode_fp8_prepare(
         # reference src/attention/entry.cc:649-652).
         task_map = get_attention_decode_task_workspace(
             num_batch, int(num_seq_max_blocks) * block_size + num_seq_q, num_head_k,
-            min_process_len=512)
+            min_process_len=512, device=q.device)
         _assign_task_cuda(num_seq_kvcache, num_head_k, num_seq_q, new_kv_included, 512, task_map)
 
     splitk = num_total_ctas
@@ -376,18 +379,19 @@ def attention_decode_fp8(
 
 
 def get_attention_decode_task_workspace(
-    max_num_batch: int, max_seqlen: int, num_head_kv: int, min_process_len: int = 512
+    max_num_batch: int, max_seqlen: int, num_head_kv: int, min_process_len: int = 512, device=None
 ):
     """Allocate (and zero) the decode task map; sizing identical to reference
     hpc/attention.py:520-582 (worst case over 64-key tiles and 1..4 CTAs per SM), so a workspace
     is interchangeable between builds.
 
-    Returns int8 [task_map_byte_size] on the current CUDA device with header ints
-    [2]=num_head_kv, [3]=max_num_batch, [4]=sched bytes.
+    Returns int8 [task_map_byte_size] on `device` (default: the current CUDA device) with header
+    ints [2]=num_head_kv, [3]=max_num_batch, [4]=sched bytes. (`device` is an extension over the
+    reference signature: the attention entry passes q.device.)
     """
     kTaskInfoByteSize = _TASK_BYTES
     kMaxCtaPerSm = 4
-    num_sm_count = _ffi.sm_count()
+    num_sm_count = _ffi.sm_count(device)
     max_num_cta_count = num_sm_count * kMaxCtaPerSm
 
     kMinTileN = 64
@@ -407,11 +411,21 @@ def get_attention_decode_task_workspace(
 
     sched_need_byte_size = max_num_tasks * kTaskInfoByteSize + max_num_batch_pad
     workspace_byte_size = sched_need_byte_size + 2 * num_cta_count_pad
-    workspace = torch.zeros(workspace_byte_size, dtype=torch.int8, device="cuda")
-    header = torch.tensor([0, 0, num_head_kv, max_num_batch, sched_need_byte_size],
-                          dtype=torch.int32)
-    workspace.view(torch.int32)[:5].copy_(header, non_blocking=False)
-    return workspace
+    # Zeroed workspace with the three header ints the scheduler reads, built without a host
+    # synchronisation: a per-(device, geometry) device-resident template is cloned (device-to-device,
+    # stream-ordered, legal under CUDA-graph capture once the template exists).
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), workspace_byte_size,
+           num_head_kv, max_num_batch, sched_need_byte_size)
+    tmpl = _WORKSPACE_TEMPLATES.get(key)
+    if tmpl is None:
+        tmpl = torch.zeros(workspace_byte_size, dtype=torch.int8, device=dev)
+        header = torch.tensor([0, 0, num_head_kv, max_num_batch, sched_need_byte_size], dtype=torch.int32)
+        tmpl.view(torch.int32)[:5].copy_(header)
+        if len(_WORKSPACE_TEMPLATES) > 64:
+            _WORKSPACE_TEMPLATES.clear()
+        _WORKSPACE_TEMPLATES[key] = tmpl
+    return tmpl.clone()
 
 
 def assign_attention_decode_task(
