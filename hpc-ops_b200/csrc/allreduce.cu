@@ -170,9 +170,10 @@ struct HtParams {
   float eps;
 };
 
-// kMode: 0 = single rank (pure residual + RMSNorm), 1 = NVLS multimem, 2 = P2P loads / stores
+// kMode: 0 = single rank (pure residual + RMSNorm), 1 = NVLS multimem, 2 = P2P on two GPUs,
+// 3 = P2P for any world size (fabrics without a multicast mapping)
 template <int NVEC, int THREADS, int kMode>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 && NVEC <= 4) ? (kMode == 0 ? 3 : (kMode <= 2 ? 2 : 1)) : 1)
     ar_rmsnorm_ht_kernel(const HtParams p) {
   constexpr int kWarps = THREADS / 32;
   __shared__ float s_red[2][kWarps];
@@ -227,10 +228,34 @@ __global__ void __launch_bounds__(THREADS)
           xv[j] = multimem_ld_reduce_bf16x8(static_cast<const __nv_bfloat16*>(p.mc_x) + roff + v * 8);
         }
       }
+    } else if constexpr (kMode == 2) {
+      // P2P on two GPUs (the transport of choice at W=2): both ranks' vectors of the row are
+      // requested before any is consumed -- a peer load takes ~2 us, so the bytes in flight decide
+      // the link utilisation -- and summed pairwise (rank 0 + rank 1, rounded to bf16 like NVLS).
+      uint4 r0[NVEC], r1[NVEC];
+#pragma unroll
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) {
+          r0[j] = ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[0]) + roff + v * 8);
+          r1[j] = ld_sys_v4(reinterpret_cast<const __nv_bfloat16*>(p.peer_x[1]) + roff + v * 8);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NVEC; j++) {
+        const int v = tid + j * THREADS;
+        if (v < nv_row) {
+          float a[8], b[8];
+          unpack8(r0[j], a);
+          unpack8(r1[j], b);
+#pragma unroll
+          for (int i = 0; i < 8; i++) a[i] += b[i];
+          xv[j] = pack8(a);
+        }
+      }
     } else {
-      // P2P: fp32 sum in rank order (deterministic), rounded to bf16 like the NVLS result. The
-      // loads of two ranks x NVEC vectors are issued before any is consumed: a peer load takes
-      // ~1 us, so the bytes in flight per thread decide the link utilisation.
+      // P2P, any world size (fabrics without an NVLS mapping): fp32 sum in rank order, two ranks'
+      // loads in flight at a time
       float acc[NVEC][8];
 #pragma unroll
       for (int j = 0; j < NVEC; j++)
@@ -602,8 +627,10 @@ struct HtLaunch {
       ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 0><<<grid, THREADS, 0, stream>>>(p);
     } else if (p.mc_x != nullptr) {
       ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 1><<<grid, THREADS, 0, stream>>>(p);
-    } else {
+    } else if (p.world == 2) {
       ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 2><<<grid, THREADS, 0, stream>>>(p);
+    } else {
+      ar::ar_rmsnorm_ht_kernel<NVEC, THREADS, 3><<<grid, THREADS, 0, stream>>>(p);
     }
     HPC_CUDA_CHECK(cudaGetLastError());
     return HPC_OK;

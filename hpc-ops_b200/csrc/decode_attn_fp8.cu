@@ -103,7 +103,7 @@ struct Smem {
 //   stage_empty[st]         tcgen05.commit after PV of the tile -> producer (K and V slots free)
 //   q_full/q_empty[qb]      Q rows of a task                    (producer <-> MMA thread)
 //   s_full[buf]             commit after QK                     -> softmax warps
-//   p_full[buf]             128 softmax threads wrote P^T       -> MMA thread
+//   p_full[buf]             the 4 softmax warps wrote P^T       -> MMA thread
 //   o_full[buf]             commit after PV                     -> softmax warps
 // No "empty" barriers are needed for S, P and O: the MMA thread issues QK(n) only after it has
 // waited p_full(n-2) (softmax threads arrive on it after their tcgen05.ld of S(n-2) and O(n-3)),
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         fence_proxy_async_smem();
         tc_fence_before();  // orders this thread's tcgen05.ld of S(n) and O(n-2) before the arrive
-        mbar_arrive(&p_full[buf]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[buf]);
 
         if (tt > 0) consume_o(n - 1);
 #pragma unroll

@@ -60,8 +60,8 @@ struct Smem {
 //   v_full/v_empty[slot]   V ring; released by the commit after PV(n). v_empty also tells the
 //                          softmax threads that PV(n) is complete (P buffer free, O consistent)
 //   s_full      commit after QK(n)                            -> softmax
-//   s_free      128 softmax threads hold S(n) in registers     -> MMA thread may issue QK(n+1)
-//   p_full      128 softmax threads wrote P(n) (and rescaled O) -> MMA thread issues PV(n)
+//   s_free      the 4 softmax warps hold S(n) in registers      -> MMA thread may issue QK(n+1)
+//   p_full      the 4 softmax warps wrote P(n) (and rescaled O) -> MMA thread issues PV(n)
 // The k-scale buffer of tile n+2 was last read by softmax(n-2), which every softmax thread
 // finished before arriving on s_free(n-1), which precedes QK(n) and so the release of K slot n%2.
 // kPoly: exponentials per group of 8 scores that take the polynomial path (0, 2 or 4)
@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(kThreads, 2)
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1 + 128);
+    mbar_init(q_empty, 1 + 4);  // MMA commit + one arrive per softmax warp
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 4);       // one arrive per softmax warp (128 per-thread arrives serialise on the barrier)
+    mbar_init(p_full, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
         for (int c = 0; c < 8; c++) tmem_anchor16(sr + c * 16);
         tc_fence_before();
-        mbar_arrive(s_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
         // ---- pass 1: dequantised (and masked) scores in place, row maximum ----
         float vmax[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -455,10 +456,12 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(p_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
         n++;
       }
-      mbar_arrive(q_empty);  // the list / work slot may be refilled by the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty);  // the list / work slot may be refilled by the producer
       // ---- epilogue: O / sum * vscale -> bf16 row ----
       if (nact > 0) {
         mbar_wait(&v_empty[(n - 1) % kStages], ((n - 1) / kStages) & 1);  // last PV of the item
