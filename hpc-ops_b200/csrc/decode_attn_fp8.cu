@@ -41,6 +41,8 @@ struct Params {
   const float* vscale;
   float* split_out;
   float* lse;
+  __nv_bfloat16* y;  // final output: tasks that are the only chunk of their (batch, kv head) write it directly
+  int ld_y;
   int num_batch;
   int num_seq_q;
   int num_head_q;
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int sw = warp - 2;             // 0..3 index for smem exchange
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float kscale = kKPerToken ? 1.f : p.kscale[0];
+    const int* chunk_table = p.task_map + kTaskStride * (ntpc1 * p.task_map[1] + 1);  // num_chunks[h * B + b]
     float out_scale = kKPerToken ? 0.f : p.vscale[0] * (1.0f / 256.0f);
 
     uint32_t n = 0;
@@ -480,6 +483,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       named_bar_sync(kSoftmaxBar, 128);
       const long long chunk_row =
           static_cast<long long>(t.ibatch) * p.max_splitk + t.ichunk;
+      // A (batch, kv head) pair that was not split needs no combine: its rows go out as bf16 right
+      // here (the same fp32 value the combine kernel would round), and the combine kernel skips
+      // pairs with one chunk. At C2 that is ~70 % of the pairs.
+      const bool single = p.y != nullptr && __ldg(chunk_table + t.ihead_kv * p.num_batch + t.ibatch) == 1;
 #pragma unroll
       for (int r = 0; r < RL; r++) {
         const int sq = r / p.group;
@@ -487,6 +494,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (sq < p.num_seq_q) {
           const float tot = red[r] + red[32 + r] + red[64 + r] + red[96 + r];
           const float inv = tot != 0.f ? rcp_approx(tot) : 0.f;
+          if (single) {
+            p.y[(static_cast<long long>(t.ibatch) * p.num_seq_q + sq) * p.ld_y +
+                (t.ihead_kv * p.group + g) * kD + row_in_tile] =
+                __float2bfloat16_rn(acc[r] * inv * out_scale);
+            continue;
+          }
           const long long orow =
               (chunk_row * p.num_seq_q + sq) * p.num_head_q + t.ihead_kv * p.group + g;
           p.split_out[orow * kD + row_in_tile] = acc[r] * inv * out_scale;
@@ -518,7 +531,7 @@ __global__ void __launch_bounds__(128)
     decode_combine_kernel(__nv_bfloat16* __restrict__ y, const float* __restrict__ split_out,
                           const float* __restrict__ lse, const int* __restrict__ task_map,
                           int num_batch, int num_seq_q, int num_head_q, int num_head_kv, int group,
-                          int max_splitk, int lse_pad, int ldY) {
+                          int max_splitk, int lse_pad, int ldY, int direct_single) {
   __shared__ float4 s_acc[4][32];
   __shared__ float s_m[4];
   __shared__ float s_l[4];
@@ -542,6 +555,7 @@ __global__ void __launch_bounds__(128)
   (void)max_batch;
   const int* chunk_table = task_map + kTaskStride * (ntpc1 * nctas + 1);
   const int nchunks = chunk_table[hkv * num_batch + b];
+  if (nchunks == 1 && direct_single) return;  // written by the attention kernel itself
 
   float m = -INFINITY;
   float l = 0.f;
@@ -668,7 +682,7 @@ static int decode_fp8_impl(
                               static_cast<__nv_bfloat16*>(y_ptr),
                               static_cast<const float*>(split_out_ptr),
                               static_cast<const float*>(lse_ptr), task_map_ptr, num_batch, num_seq_q,
-                              num_head_q, num_head_k, group, splitk, lse_pad_, ldY));
+                              num_head_q, num_head_k, group, splitk, lse_pad_, ldY, 1));
     return HPC_OK;
   }
 
@@ -741,6 +755,8 @@ static int decode_fp8_impl(
   p.vscale = vscale_ptr;
   p.split_out = static_cast<float*>(split_out_ptr);
   p.lse = static_cast<float*>(lse_ptr);
+  p.y = static_cast<__nv_bfloat16*>(y_ptr);
+  p.ld_y = ldY;
   p.num_batch = num_batch;
   p.num_seq_q = num_seq_q;
   p.num_head_q = num_head_q;
@@ -783,7 +799,7 @@ static int decode_fp8_impl(
   HPC_CUDA_CHECK(launch_pdl(decode::decode_combine_kernel, dim3(out_rows), dim3(128), 0, stream, 1,
                             static_cast<__nv_bfloat16*>(y_ptr), static_cast<const float*>(p.split_out),
                             static_cast<const float*>(p.lse), task_map_ptr, num_batch, num_seq_q,
-                            num_head_q, num_head_k, group, splitk, p.lse_pad, ldY));
+                            num_head_q, num_head_k, group, splitk, p.lse_pad, ldY, 1));
   return HPC_OK;
 }
 
