@@ -267,6 +267,196 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// head dim 128 (the hot path's only head size): a lane owns 4 consecutive dims -- lanes 0-15 the
+// lower rotation half, lanes 16-31 the upper one, partner = lane ^ 16 -- so a head row is ONE
+// 256-byte coalesced load (8 B per lane) and one 8-byte (bf16) / 4-byte (fp8) store per lane; a warp
+// handles 8 heads with all loads issued first. The generic kernel above keeps 4-byte accesses.
+// ------------------------------------------------------------------------------------------------
+template <bool kFp8>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    rope_norm_store_kv_d128_kernel(const Params p) {
+  using OutT = typename std::conditional<kFp8, uint8_t, __nv_bfloat16>::type;
+  constexpr int kU = 8, D = 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int qg = (p.hq + kU - 1) / kU, kg = (p.hkv + kU - 1) / kU;
+  const int units = qg + kg + 1;
+  const long long items = static_cast<long long>(p.num_rows) * units;
+
+  pdl_wait();
+  pdl_launch_dependents();
+  if (kFp8 && p.split_k_flag != nullptr) {
+    const long long n = static_cast<long long>(p.num_req) * p.hkv;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      p.split_k_flag[i] = 0;
+    }
+  }
+  if (warp_global >= items) return;
+  const int row = static_cast<int>(warp_global / units);
+  const int unit = static_cast<int>(warp_global % units);
+  int lo = 0, hi = p.num_req;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(p.q_index + mid) <= row) {
+      lo = mid;
+    } else {
+      hi = mid - 1;
+    }
+  }
+  const int req = lo;
+  if (req >= p.num_req) return;
+  const int q0 = __ldg(p.q_index + req), q1 = __ldg(p.q_index + req + 1);
+  if (row < q0 || row >= q1) return;
+  const int sl = __ldg(p.seqlen + req);
+  const int pos = sl - (q1 - q0) + (row - q0);
+  if (pos < 0) return;
+
+  const long long row_elems = static_cast<long long>(p.hq) * D + static_cast<long long>(p.hkv) * (D + p.dv);
+  const __nv_bfloat16* src = p.qkv + static_cast<long long>(row) * row_elems;
+  const bool is_q = unit < qg;
+  const bool is_k = !is_q && unit < qg + kg;
+  const int bi = pos / p.block_size, pb = pos - bi * p.block_size;
+  long long cb = 0;
+  if (!is_q) cb = __ldg(p.kv_indices + static_cast<long long>(req) * p.max_blocks + bi);
+  const bool last_tok = pos == sl - 1;
+
+  if (!is_q && !is_k) {
+    const int n = p.hkv * p.dv;
+    const __nv_bfloat16* v = src + static_cast<long long>(p.hq + p.hkv) * D;
+    OutT* dst = p.out_v != nullptr
+                    ? static_cast<OutT*>(p.out_v) + static_cast<long long>(row) * n
+                    : static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride + static_cast<long long>(pb) * n;
+    const float mult = kFp8 ? __frcp_rn(__ldg(p.v_scale)) : 1.f;
+    for (int e = lane * 8; e < n; e += 256) {
+      const uint4 raw = ld_nc_v4(v + e);
+      if constexpr (kFp8) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+        const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+        uint2 o;
+        o.x = cvt_e4m3x4(f0.x * mult, f0.y * mult, f1.x * mult, f1.y * mult);
+        o.y = cvt_e4m3x4(f2.x * mult, f2.y * mult, f3.x * mult, f3.y * mult);
+        *reinterpret_cast<uint2*>(dst + e) = o;
+      } else {
+        *reinterpret_cast<uint4*>(dst + e) = raw;
+      }
+    }
+    if (p.out_v == nullptr && last_tok) {
+      OutT* z = static_cast<OutT*>(p.vcache) + cb * p.vcache_block_stride + static_cast<long long>(pb + 1) * n;
+      const long long cnt = static_cast<long long>(p.block_size - pb - 1) * n;  // multiple of 8 elements
+      constexpr int kVec = kFp8 ? 16 : 8;  // elements per 16-byte store
+      for (long long e = static_cast<long long>(lane) * kVec; e < cnt; e += 32 * kVec) {
+        if (e + kVec <= cnt) {
+          *reinterpret_cast<uint4*>(z + e) = make_uint4(0, 0, 0, 0);
+        } else {
+          for (long long t2 = e; t2 < cnt; t2 += 2) store2<OutT>(z + t2, 0.f, 0.f);
+        }
+      }
+    }
+    return;
+  }
+
+  const int nheads = is_q ? p.hq : p.hkv;
+  const int h0 = (is_q ? unit : unit - qg) * kU;
+  const __nv_bfloat16* xbase = src + (is_q ? 0ll : static_cast<long long>(p.hq) * D);
+  const int hi_half = lane >> 4;
+  const int idx = 4 * (lane & 15);          // dim inside the rotation half
+  const int dim0 = hi_half * 64 + idx;      // dim inside the head
+  uint2 raw[kU];
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    raw[u] = make_uint2(0, 0);
+    if (h0 + u < nheads) raw[u] = *reinterpret_cast<const uint2*>(xbase + static_cast<long long>(h0 + u) * D + dim0);
+  }
+  const float4 co = *reinterpret_cast<const float4*>(p.cos_sin + static_cast<long long>(pos) * D + idx);
+  const float4 si = *reinterpret_cast<const float4*>(p.cos_sin + static_cast<long long>(pos) * D + 64 + idx);
+  const float sgn = hi_half ? 1.f : -1.f;   // lower half: x1 c - x2 s ; upper half: x2 c + x1 s
+  float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.norm_policy != 0) w = *reinterpret_cast<const float4*>((is_q ? p.q_norm_w : p.k_norm_w) + dim0);
+  const float k_mult = (kFp8 && !is_q) ? __frcp_rn(__ldg(p.k_scale)) : 1.f;
+
+#pragma unroll
+  for (int u = 0; u < kU; u++) {
+    if (h0 + u >= nheads) break;  // warp-uniform
+    const int head = h0 + u;
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+    const float2 f01 = __bfloat1622float2(hb[0]), f23 = __bfloat1622float2(hb[1]);
+    float v[4] = {f01.x, f01.y, f23.x, f23.y};
+    auto rms = [&]() {
+      const float ssq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+      const float r = rsqrtf(warp_sum_f32(ssq) / 128.f + 1e-6f);
+      v[0] *= r * w.x; v[1] *= r * w.y; v[2] *= r * w.z; v[3] *= r * w.w;
+    };
+    if (p.norm_policy == 2) rms();
+    {
+      const float o0 = __shfl_xor_sync(0xffffffffu, v[0], 16), o1 = __shfl_xor_sync(0xffffffffu, v[1], 16);
+      const float o2 = __shfl_xor_sync(0xffffffffu, v[2], 16), o3 = __shfl_xor_sync(0xffffffffu, v[3], 16);
+      v[0] = v[0] * co.x + sgn * o0 * si.x;
+      v[1] = v[1] * co.y + sgn * o1 * si.y;
+      v[2] = v[2] * co.z + sgn * o2 * si.z;
+      v[3] = v[3] * co.w + sgn * o3 * si.w;
+    }
+    if (p.norm_policy == 1) rms();
+    float mult = k_mult;
+    if (kFp8 && is_q) {
+      if (p.quant_policy == 1) {
+        const float m = warp_max_f32(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
+        const float qs = m / p.upper_max;
+        if (lane == 0) {
+          if (p.is_prefill) {
+            p.q_scale[(static_cast<long long>(req) * p.hq + head) * p.max_seqlen_aligned + (row - q0)] = qs;
+          } else {
+            p.q_scale[static_cast<long long>(row) * p.hq + head] = qs;
+          }
+        }
+        mult = qs > 0.f ? __frcp_rn(qs) : 0.f;
+      } else {
+        mult = __ldg(p.q_scale_inv);
+      }
+    }
+    OutT* dst;
+    if (is_q) {
+      dst = static_cast<OutT*>(p.out_q) + (static_cast<long long>(row) * p.hq + head) * D;
+    } else if (p.out_k != nullptr) {
+      dst = static_cast<OutT*>(p.out_k) + (static_cast<long long>(row) * p.hkv + head) * D;
+    } else {
+      dst = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + (static_cast<long long>(pb) * p.hkv + head) * D;
+    }
+    if constexpr (kFp8) {
+      *reinterpret_cast<uint32_t*>(dst + dim0) = cvt_e4m3x4(v[0] * mult, v[1] * mult, v[2] * mult, v[3] * mult);
+    } else {
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&b0);
+      o.y = *reinterpret_cast<uint32_t*>(&b1);
+      *reinterpret_cast<uint2*>(dst + dim0) = o;
+    }
+  }
+  if (is_k && unit == qg && p.out_k == nullptr && last_tok) {
+    const int n = p.hkv * D;
+    OutT* z = static_cast<OutT*>(p.kcache) + cb * p.kcache_block_stride + static_cast<long long>(pb + 1) * n;
+    const long long cnt = static_cast<long long>(p.block_size - pb - 1) * n;  // multiple of 128 elements
+    constexpr int kVec = kFp8 ? 16 : 8;
+    for (long long e = static_cast<long long>(lane) * kVec; e < cnt; e += 32 * kVec) {
+      *reinterpret_cast<uint4*>(z + e) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+template <bool kFp8>
+static int launch_d128(const Params& p, cudaStream_t stream) {
+  constexpr int kU = 8;
+  const long long units = (p.hq + kU - 1) / kU + (p.hkv + kU - 1) / kU + 1;
+  const long long items = static_cast<long long>(p.num_rows) * units;
+  const long long blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  HPC_REQUIRE(blocks < (1ll << 31), "rope: too many rows");
+  HPC_CUDA_CHECK(launch_pdl(rope_norm_store_kv_d128_kernel<kFp8>, dim3(static_cast<unsigned>(blocks)),
+                            dim3(kWarpsPerBlock * 32), 0, stream, 1, p));
+  return HPC_OK;
+}
+
 template <bool kFp8, int kCH>
 static int launch_impl(const Params& p, cudaStream_t stream) {
   constexpr int kU = 4 / kCH;
@@ -288,6 +478,16 @@ static int launch(bool fp8, const Params& p, cudaStream_t stream) {
     HPC_REQUIRE(p.q_norm_w != nullptr && p.k_norm_w != nullptr, "rope: norm weights required");
   }
   if (p.num_rows <= 0) return HPC_OK;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(p.qkv) | reinterpret_cast<uintptr_t>(p.cos_sin) |
+                           reinterpret_cast<uintptr_t>(p.out_q) | reinterpret_cast<uintptr_t>(p.kcache) |
+                           reinterpret_cast<uintptr_t>(p.vcache) | reinterpret_cast<uintptr_t>(p.out_k) |
+                           reinterpret_cast<uintptr_t>(p.out_v) | reinterpret_cast<uintptr_t>(p.q_norm_w) |
+                           reinterpret_cast<uintptr_t>(p.k_norm_w)) & 15) == 0;
+  const int out_bytes = fp8 ? 1 : 2;
+  if (p.dqk == 128 && p.dv % 16 == 0 && aligned16 && (p.kcache_block_stride * out_bytes) % 16 == 0 &&
+      (p.vcache_block_stride * out_bytes) % 16 == 0) {
+    return fp8 ? launch_d128<true>(p, stream) : launch_d128<false>(p, stream);
+  }
   const int ch = (p.dqk / 2 + 63) / 64;  // 64-dim chunks per rotation half
   if (fp8) {
     if (ch <= 1) return launch_impl<true, 1>(p, stream);
