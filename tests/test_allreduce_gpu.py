@@ -108,6 +108,9 @@ def _run_ll(rank, world, seq, hidden, big_ws, two_shot, port, q):
 def _spawn(target, world, args):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    only = os.environ.get("HPC_B200_TEST_WORLDS")  # e.g. "4,8" on a multi-GPU lease: skip the rest
+    if only and str(world) not in only.split(","):
+        pytest.skip(f"world size {world} not selected by HPC_B200_TEST_WORLDS")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 21000 + (os.getpid() * 7 + hash(args) % 997) % 15000
