@@ -19,69 +19,13 @@
 //   src/attention/decode/decode.h:28-37 (attention_decode_fp8_async).
 #include <cstdlib>
 
-#include "common.cuh"
-#include "host_utils.h"
+#include "decode_common.cuh"
 
 namespace b200 {
 namespace decode {
 
-constexpr int kTileN = 128;  // keys per tile == UMMA M
-constexpr int kPage = 64;    // paged block size (tokens)
-constexpr int kD = 128;      // head dim
 constexpr int kSlotBytes = kTileN * kD;  // 16 KB (fp8)
 constexpr int kThreads = 192;
-constexpr int kTaskStride = 12;
-constexpr int kSoftmaxBar = 1;
-
-struct Params {
-  const int* task_map;
-  const int* block_ids;
-  const float* qscale;
-  const float* kscale;
-  const float* vscale;
-  float* split_out;
-  float* lse;
-  __nv_bfloat16* y;  // final output: tasks that are the only chunk of their (batch, kv head) write it directly
-  int ld_y;
-  int num_batch;
-  int num_seq_q;
-  int num_head_q;
-  int num_head_kv;
-  int group;
-  int num_seq_max_blocks;
-  int qscale_stride;
-  int max_splitk;
-  int lse_pad;
-  int k_head_first;  // TMA dim order of the cache maps: (d, head, token, blk) or (d, token, head, blk)
-  int v_head_first;
-  float softmax_scale_log2;
-  // k-per-token variant: in-cache scale rows: float index
-  //   blk * ks_blk + (t / 32) * ks_row + head * ks_head + t % 32     (t = token slot in the page)
-  long long ks_blk, ks_row, ks_head;
-};
-
-struct Task {
-  int ihead_kv, ibatch, ichunk, iseq_start;
-  int num_seqkv, num_seqkvcache, num_tile_kv, num_tile_full;
-  int is_causal;
-};
-
-__device__ __forceinline__ bool load_task(const int* row, Task& t) {
-  int4 a = *reinterpret_cast<const int4*>(row);
-  if (a.x < 0 || a.y < 0) return false;
-  int4 b = *reinterpret_cast<const int4*>(row + 4);
-  int c = row[8];
-  t.ihead_kv = a.x;
-  t.ibatch = a.y;
-  t.ichunk = a.z;
-  t.iseq_start = a.w;
-  t.num_seqkv = b.x;
-  t.num_seqkvcache = b.y;
-  t.num_tile_kv = b.z;
-  t.num_tile_full = b.w;
-  t.is_causal = c;
-  return true;
-}
 
 constexpr int kNumStages = 6;                 // (K tile + V tile) stages of 32 KB
 constexpr int kStageBytes = 2 * kSlotBytes;
@@ -608,6 +552,16 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+cudaError_t launch_combine(__nv_bfloat16* y, const float* split_out, const float* lse,
+                           const int* task_map, int num_batch, int num_seq_q, int num_head_q,
+                           int num_head_kv, int group, int max_splitk, int lse_pad, int ldY,
+                           cudaStream_t stream) {
+  const int out_rows = num_batch * num_seq_q * num_head_q;
+  return launch_pdl(decode_combine_kernel, dim3(out_rows), dim3(128), 0, stream, 1, y, split_out, lse,
+                    task_map, num_batch, num_seq_q, num_head_q, num_head_kv, group, max_splitk,
+                    lse_pad, ldY, 1);
+}
+
 template <int NQ, int RL, bool kKPerToken>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const Params& p, int grid, cudaStream_t stream) {
@@ -677,12 +631,11 @@ static int decode_fp8_impl(
 
   const int lse_pad_ = (group + 7) / 8 * 8;
   if (run_combine && !run_attn) {
-    const int out_rows_ = num_batch * num_seq_q * num_head_q;
-    HPC_CUDA_CHECK(launch_pdl(decode::decode_combine_kernel, dim3(out_rows_), dim3(128), 0, stream, 1,
-                              static_cast<__nv_bfloat16*>(y_ptr),
-                              static_cast<const float*>(split_out_ptr),
-                              static_cast<const float*>(lse_ptr), task_map_ptr, num_batch, num_seq_q,
-                              num_head_q, num_head_k, group, splitk, lse_pad_, ldY, 1));
+    HPC_CUDA_CHECK(decode::launch_combine(static_cast<__nv_bfloat16*>(y_ptr),
+                                          static_cast<const float*>(split_out_ptr),
+                                          static_cast<const float*>(lse_ptr), task_map_ptr, num_batch,
+                                          num_seq_q, num_head_q, num_head_k, group, splitk, lse_pad_,
+                                          ldY, stream));
     return HPC_OK;
   }
 
@@ -795,11 +748,9 @@ static int decode_fp8_impl(
   if (rc) return rc;
   if (!run_combine) return HPC_OK;
 
-  const int out_rows = num_batch * num_seq_q * num_head_q;
-  HPC_CUDA_CHECK(launch_pdl(decode::decode_combine_kernel, dim3(out_rows), dim3(128), 0, stream, 1,
-                            static_cast<__nv_bfloat16*>(y_ptr), static_cast<const float*>(p.split_out),
-                            static_cast<const float*>(p.lse), task_map_ptr, num_batch, num_seq_q,
-                            num_head_q, num_head_k, group, splitk, p.lse_pad, ldY, 1));
+  HPC_CUDA_CHECK(decode::launch_combine(static_cast<__nv_bfloat16*>(y_ptr), p.split_out, p.lse,
+                                        task_map_ptr, num_batch, num_seq_q, num_head_q, num_head_k,
+                                        group, splitk, p.lse_pad, ldY, stream));
   return HPC_OK;
 }
 

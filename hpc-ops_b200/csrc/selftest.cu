@@ -10,12 +10,16 @@ namespace selftest {
 constexpr int kMaxA = 65536;
 constexpr int kMaxB = 32768;
 
+// kF16: kind::f16 (bf16 operands) instead of kind::f8f6f4. K step k reads its operands at
+// (k / nk_inner) * kstep2 + (k % nk_inner) * kstep (two-level walk: 64-element swizzle atoms).
+template <bool kF16>
 __global__ void __launch_bounds__(128, 1)
-    umma_f8_kernel(const uint8_t* __restrict__ a_image, int a_bytes,
+    umma_kernel(const uint8_t* __restrict__ a_image, int a_bytes,
                    const uint8_t* __restrict__ b_image, int b_bytes, float* __restrict__ d_out,
                    int ncols, uint32_t idesc, int nk, uint32_t a_lbo, uint32_t a_sbo,
                    uint32_t a_layout, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
-                   uint32_t b_layout, uint32_t b_kstep) {
+                   uint32_t b_layout, uint32_t b_kstep, int nk_inner, uint32_t a_kstep2,
+                   uint32_t b_kstep2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sa = smem;
   uint8_t* sb = smem + kMaxA;
@@ -46,9 +50,16 @@ __global__ void __launch_bounds__(128, 1)
 
   if (tid == 0) {
     for (int k = 0; k < nk; k++) {
-      const uint64_t ad = make_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo, a_layout);
-      const uint64_t bd = make_smem_desc(smem_u32(sb) + k * b_kstep, b_lbo, b_sbo, b_layout);
-      umma_f8(tmem_base, ad, bd, idesc, k > 0);
+      const uint32_t ko = k / nk_inner, ki = k % nk_inner;
+      const uint64_t ad =
+          make_smem_desc(smem_u32(sa) + ko * a_kstep2 + ki * a_kstep, a_lbo, a_sbo, a_layout);
+      const uint64_t bd =
+          make_smem_desc(smem_u32(sb) + ko * b_kstep2 + ki * b_kstep, b_lbo, b_sbo, b_layout);
+      if constexpr (kF16) {
+        umma_f16(tmem_base, ad, bd, idesc, k > 0);
+      } else {
+        umma_f8(tmem_base, ad, bd, idesc, k > 0);
+      }
     }
     umma_commit(bar);
   }
@@ -299,26 +310,51 @@ __global__ void __launch_bounds__(kProbeThreads, 1)
 
 using namespace b200;  // NOLINT
 
+template <bool kF16>
+static int run_umma_selftest(const void* a_image, int a_bytes, const void* b_image, int b_bytes,
+                             float* d_out, int ncols, uint32_t idesc, int nk, uint32_t a_lbo,
+                             uint32_t a_sbo, uint32_t a_layout, uint32_t a_kstep, uint32_t b_lbo,
+                             uint32_t b_sbo, uint32_t b_layout, uint32_t b_kstep, int nk_inner,
+                             uint32_t a_kstep2, uint32_t b_kstep2, cudaStream_t stream) {
+  HPC_REQUIRE(a_bytes > 0 && a_bytes <= selftest::kMaxA && a_bytes % 16 == 0, "bad a_bytes");
+  HPC_REQUIRE(b_bytes > 0 && b_bytes <= selftest::kMaxB && b_bytes % 16 == 0, "bad b_bytes");
+  HPC_REQUIRE(ncols > 0 && ncols <= 256, "bad ncols");
+  HPC_REQUIRE(nk > 0 && nk_inner > 0, "bad nk");
+  const int smem = selftest::kMaxA + selftest::kMaxB + 64;
+  static bool configured = false;
+  if (!configured) {
+    HPC_CUDA_CHECK(cudaFuncSetAttribute(selftest::umma_kernel<kF16>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  selftest::umma_kernel<kF16><<<1, 128, smem, stream>>>(
+      static_cast<const uint8_t*>(a_image), a_bytes, static_cast<const uint8_t*>(b_image), b_bytes,
+      d_out, ncols, idesc, nk, a_lbo, a_sbo, a_layout, a_kstep, b_lbo, b_sbo, b_layout, b_kstep,
+      nk_inner, a_kstep2, b_kstep2);
+  HPC_CUDA_CHECK(cudaGetLastError());
+  return HPC_OK;
+}
+
 extern "C" int hpc_selftest_umma_f8(const void* a_image, int a_bytes, const void* b_image,
                                     int b_bytes, float* d_out, int ncols, uint32_t idesc, int nk,
                                     uint32_t a_lbo, uint32_t a_sbo, uint32_t a_layout,
                                     uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
                                     uint32_t b_layout, uint32_t b_kstep, cudaStream_t stream) {
-  HPC_REQUIRE(a_bytes > 0 && a_bytes <= selftest::kMaxA && a_bytes % 16 == 0, "bad a_bytes");
-  HPC_REQUIRE(b_bytes > 0 && b_bytes <= selftest::kMaxB && b_bytes % 16 == 0, "bad b_bytes");
-  HPC_REQUIRE(ncols > 0 && ncols <= 256, "bad ncols");
-  const int smem = selftest::kMaxA + selftest::kMaxB + 64;
-  static bool configured = false;
-  if (!configured) {
-    HPC_CUDA_CHECK(cudaFuncSetAttribute(selftest::umma_f8_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  selftest::umma_f8_kernel<<<1, 128, smem, stream>>>(
-      static_cast<const uint8_t*>(a_image), a_bytes, static_cast<const uint8_t*>(b_image), b_bytes,
-      d_out, ncols, idesc, nk, a_lbo, a_sbo, a_layout, a_kstep, b_lbo, b_sbo, b_layout, b_kstep);
-  HPC_CUDA_CHECK(cudaGetLastError());
-  return HPC_OK;
+  return run_umma_selftest<false>(a_image, a_bytes, b_image, b_bytes, d_out, ncols, idesc, nk, a_lbo,
+                                  a_sbo, a_layout, a_kstep, b_lbo, b_sbo, b_layout, b_kstep, nk, 0, 0,
+                                  stream);
+}
+
+// bf16 operands (kind::f16); K step k reads at (k / nk_inner) * kstep2 + (k % nk_inner) * kstep
+extern "C" int hpc_selftest_umma_bf16(const void* a_image, int a_bytes, const void* b_image,
+                                      int b_bytes, float* d_out, int ncols, uint32_t idesc, int nk,
+                                      uint32_t a_lbo, uint32_t a_sbo, uint32_t a_layout,
+                                      uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
+                                      uint32_t b_layout, uint32_t b_kstep, int nk_inner,
+                                      uint32_t a_kstep2, uint32_t b_kstep2, cudaStream_t stream) {
+  return run_umma_selftest<true>(a_image, a_bytes, b_image, b_bytes, d_out, ncols, idesc, nk, a_lbo,
+                                 a_sbo, a_layout, a_kstep, b_lbo, b_sbo, b_layout, b_kstep, nk_inner,
+                                 a_kstep2, b_kstep2, stream);
 }
 
 // diagnostics: UMMA issue rate. pair = 0 / 1 (cta_group::1 / ::2), n = MMA N (16..256), flags: see

@@ -41,6 +41,9 @@ lib.hpc_attention_decode_fp8_async.argtypes = (
     [c_ptr] * 13 + [c_int] * 18 + [c_i64] * 6 + [c_ptr]
 )
 
+lib.hpc_attention_decode_bf16_async.restype = c_int
+lib.hpc_attention_decode_bf16_async.argtypes = [c_ptr] * 10 + [c_int] * 14 + [c_i64] * 6 + [c_ptr]
+
 for _n in ("hpc_attention_decode_fp8_partial_async", "hpc_attention_decode_fp8_combine_async"):
     getattr(lib, _n).restype = c_int
     getattr(lib, _n).argtypes = lib.hpc_attention_decode_fp8_async.argtypes
@@ -99,6 +102,11 @@ lib.hpc_attention_blocksparse_prefill_qkpertoken_perhead_vperhead_fp8_async.argt
 lib.hpc_selftest_umma_f8.restype = c_int
 lib.hpc_selftest_umma_f8.argtypes = (
     [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_ptr]
+)
+lib.hpc_selftest_umma_bf16.restype = c_int
+lib.hpc_selftest_umma_bf16.argtypes = (
+    [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_u32, c_int] + [c_u32] * 8 + [c_int, c_u32, c_u32]
+    + [c_ptr]
 )
 # (hasattr: tools/r2_ab.sh swaps in libraries built from older commits for on-box A/B timing; a
 # library without these symbols still fails loudly -- at the first rope call)

@@ -149,6 +149,78 @@ def _decode_fp8_prepare(
     return y, args, (lse, split_out, task_map)
 
 
+def _attention_decode_bf16_impl(
+    q, kcache, vcache, block_ids, num_seq_kvcache, mtp, new_kv_included, use_splitk,
+    task_map=None, split_flag=None, output=None,
+):
+    """bf16 paged decode attention; validation mirrors reference src/attention/entry.cc:411-470."""
+    _require(q.is_cuda, "q tensor must be cuda")
+    _require(kcache.is_cuda, "kcache tensor must be cuda")
+    _require(vcache.is_cuda, "vcache tensor must be cuda")
+    _require(block_ids.is_cuda, "block_ids tensor must be cuda")
+    _require(block_ids.is_contiguous(), "block_ids tensor must be contiguous")
+    _require(num_seq_kvcache.is_contiguous(), "num_seq_kvcache tensor must be contiguous")
+    _require(block_ids.dtype == torch.int32, "block_ids dtype must be int32")
+    _require(num_seq_kvcache.dtype == torch.int32, "num_seq_kvcache dtype must be int32")
+    _require(mtp in (0, 1, 2, 3, 4), "we only support mtp 0, 1, 2, 3, 4.")
+    _require(q.dtype == torch.bfloat16 and kcache.dtype == torch.bfloat16
+             and vcache.dtype == torch.bfloat16, "q, kcache and vcache must be bfloat16")
+
+    num_batch = num_seq_kvcache.size(0)
+    num_seq_q = q.size(0) // num_batch
+    _require(num_seq_q == mtp + 1, "every request num_seq_q must be mtp + 1")
+    num_head_q = q.size(1)
+    num_dim_qk = q.size(2)
+    _require(num_dim_qk == 128, "we only support head dim 128.")
+    num_kvcache_blocks = kcache.size(0)
+    block_size = kcache.size(1)
+    _require(block_size in (16, 32, 64), "kvcache paged blocksize must be 16, 32 or 64.")
+    num_head_k = kcache.size(2)
+    num_head_v = vcache.size(2)
+    num_dim_v = vcache.size(3)
+    num_seq_max_blocks = block_ids.size(1)
+    heads_per_group = num_head_q // num_head_k
+    _require(heads_per_group in (4, 8), "we only support num_head_q / num_head_k == 4 or 8.")
+    _require(heads_per_group * num_seq_q <= 32,
+             "heads_per_group * num_seq_q must be <= 32 on sm_100 (mtp 4 needs heads_per_group 4)")
+    _require(q.stride(2) == 1 and q.stride(1) == num_dim_qk, "q must be contiguous in (head, dim)")
+    _require(kcache.stride(3) == 1 and vcache.stride(3) == 1, "kv cache innermost dim must be contiguous")
+
+    if output is not None:
+        y = output
+    else:
+        y = torch.empty((num_batch * num_seq_q, num_head_q, num_dim_v), dtype=torch.bfloat16,
+                        device=q.device)
+
+    num_total_ctas = _num_total_ctas(q.device)
+    if task_map is None:
+        # task-map driven kernel: without a caller-provided map the schedule is made on the device
+        # right here (the reference's static split-k path, src/attention/entry.cc:540-570)
+        task_map = get_attention_decode_task_workspace(
+            num_batch, int(num_seq_max_blocks) * block_size + num_seq_q, num_head_k,
+            min_process_len=512, device=q.device)
+        _assign_task_cuda(num_seq_kvcache, num_head_k, num_seq_q, new_kv_included, 512, task_map)
+    else:
+        _require(bool(use_splitk), "attention_decode_bf16: splitk must be true with a task_map.")
+
+    splitk = num_total_ctas
+    pad_heads_per_group = (heads_per_group + 7) // 8 * 8
+    lse = torch.empty((num_batch, splitk, num_head_k, num_seq_q, pad_heads_per_group),
+                      dtype=torch.float32, device=q.device)
+    split_out = torch.empty((num_batch, splitk, num_seq_q, num_head_q, num_dim_v),
+                            dtype=torch.float32, device=q.device)
+    _check_rc(_lib.hpc_attention_decode_bf16_async(
+        _ptr(y), _ptr(lse), _ptr(split_out), _ptr(task_map), _ptr(q), _ptr(kcache), _ptr(vcache),
+        _ptr(block_ids), _ptr(num_seq_kvcache), _ptr(split_flag),
+        int(bool(new_kv_included)), splitk,
+        num_batch, num_seq_q, num_head_q, num_head_k, num_head_v, num_dim_qk, num_dim_v,
+        num_kvcache_blocks, block_size, num_seq_max_blocks, y.stride(0), q.stride(0),
+        kcache.stride(0), kcache.stride(1), kcache.stride(2),
+        vcache.stride(0), vcache.stride(1), vcache.stride(2),
+        _stream_of(q)), "attention_decode_bf16")
+    return y
+
+
 def _assign_task_cpu(num_seq_kvcache, num_head_kv, num_seq_q, new_kv_included, min_process_len,
                      placeholder=None, num_total_ctas: _Optional[int] = None):
     """CPU scheduler -> packed host task map int8 [rows, 48] (reference entry.cc:727-778)."""
@@ -271,6 +343,13 @@ _ops.define(
 _ops.impl("attention_with_kvcache_prefill_fp8", _dense_prefill_fp8_impl, "CUDA")
 
 _ops.define(
+    "attention_decode_bf16(Tensor q, Tensor! kcache, Tensor! vcache, Tensor block_ids, Tensor "
+    "num_seq_kvcache, int mtp, bool new_kv_included, bool use_splitk, Tensor? task_map, "
+    "Tensor? split_flag, Tensor? output) -> "
+    "(Tensor)")
+_ops.impl("attention_decode_bf16", _attention_decode_bf16_impl, "CUDA")
+
+_ops.define(
     "attention_decode_fp8(Tensor q, Tensor! kcache, Tensor! vcache, Tensor block_ids, Tensor "
     "num_seq_kvcache, Tensor qscale, Tensor kscale, Tensor vscale, int mtp, bool "
     "new_kv_included, int quant_type, bool "
@@ -339,6 +418,37 @@ def attention_with_kvcache_blocksparse_prefill_fp8(
     return torch.ops.hpc.attention_with_kvcache_blocksparse_prefill_fp8(
         q, kcache, vcache, qscale, kscale, vscale, cu_seqlens_q, block_ids, seqlens_kvcache,
         max_seqlens_q, quant_type.value, block_mask, output)
+
+
+def attention_decode_bf16(
+    q: Tensor,
+    kcache: Tensor,
+    vcache: Tensor,
+    block_ids: Tensor,
+    num_seq_kvcache: Tensor,
+    mtp: int = 0,
+    new_kv_included: bool = False,
+    splitk: bool = True,
+    task_map: Tensor = None,
+    split_flag: Tensor = None,
+    output: Tensor = None,
+) -> Tensor:
+    """BF16 paged decode attention: softmax(Q K^T / sqrt(d)) V with the MTP causal tail.
+
+    Same contract as reference hpc/attention.py:341-417.
+      q          [num_batch * num_seq_q, num_head_q, 128] bfloat16 (num_seq_q = mtp + 1)
+      kcache     [num_blocks, block_size, num_head_kv, 128] bfloat16, block_size 16 / 32 / 64, any
+                 strides on dims 0-2 (NHD or HND); unused slots of a request's last block zero
+      vcache     same
+      block_ids  [num_batch, max_blocks] int32;  num_seq_kvcache [num_batch] int32
+      task_map   from get_attention_decode_task_workspace + assign_attention_decode_task (None:
+                 scheduled on the device inside the call)
+    Returns bf16 [num_batch * num_seq_q, num_head_q, 128].
+    """
+    return torch.ops.hpc.attention_decode_bf16(
+        q, kcache, vcache, block_ids, num_seq_kvcache, mtp, new_kv_included, splitk, task_map,
+        split_flag, output,
+    )
 
 
 def attention_decode_fp8(
@@ -502,6 +612,16 @@ def _dense_prefill_fp8_fake(q, kcache, vcache, qscale, kscale, vscale, cu_seqlen
     if output is not None:
         return output
     return torch.empty((q.size(0), q.size(1), vcache.size(3)), dtype=torch.bfloat16, device=q.device)
+
+
+@torch.library.register_fake("hpc::attention_decode_bf16")
+def _attention_decode_bf16_fake(
+    q, kcache, vcache, block_ids, num_seq_kvcache, mtp, new_kv_included, use_splitk,
+    task_map=None, split_flag=None, output=None,
+):
+    if output is not None:
+        return output
+    return torch.empty_like(q)
 
 
 @torch.library.register_fake("hpc::attention_decode_fp8")

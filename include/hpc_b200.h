@@ -79,6 +79,19 @@ int hpc_attention_decode_fp8_async(
     int64_t kcache_token_stride, int64_t kcache_head_stride, int64_t vcache_block_stride,
     int64_t vcache_token_stride, int64_t vcache_head_stride, cudaStream_t stream);
 
+/* ---- decode attention: BF16 paged KV (block size 16 / 32 / 64) --------------------------------
+ * replaces reference src/attention/decode/decode.h:16-25 (attention_decode_bf16_async); argument
+ * order and meaning are identical (strides in bf16 elements). lse / split_out as above. */
+int hpc_attention_decode_bf16_async(
+    void* y_ptr, void* lse_ptr, void* split_out_ptr, const int* task_map_ptr, const void* q_ptr,
+    void* kcache_ptr, void* vcache_ptr, const int* block_ids_ptr, const int* num_seq_kvcache_ptr,
+    int* split_flag_ptr, int new_kv_included, int splitk, int num_batch, int num_seq_q,
+    int num_head_q, int num_head_k, int num_head_v, int num_dim_qk, int num_dim_v,
+    int num_kvcache_blocks, int block_size, int num_seq_max_blocks, int ldY, int ldQ,
+    int64_t kcache_block_stride, int64_t kcache_token_stride, int64_t kcache_head_stride,
+    int64_t vcache_block_stride, int64_t vcache_token_stride, int64_t vcache_head_stride,
+    cudaStream_t stream);
+
 /* The two stages of hpc_attention_decode_fp8_async on their own, same argument list: the split-k
  * attention kernel (writes lse / split_out) and the LSE combine (reads them, writes y). The
  * reference launches them back to back inside one launcher
@@ -292,6 +305,15 @@ int hpc_selftest_umma_f8(const void* a_image, int a_bytes, const void* b_image, 
                          float* d_out, int ncols, uint32_t idesc, int nk, uint32_t a_lbo,
                          uint32_t a_sbo, uint32_t a_layout, uint32_t a_kstep, uint32_t b_lbo,
                          uint32_t b_sbo, uint32_t b_layout, uint32_t b_kstep, cudaStream_t stream);
+
+/* Same with bf16 operands (kind::f16). K step k reads its operands at
+ * (k / nk_inner) * kstep2 + (k % nk_inner) * kstep: a 128-wide bf16 K extent is two 64-element
+ * swizzle atoms. */
+int hpc_selftest_umma_bf16(const void* a_image, int a_bytes, const void* b_image, int b_bytes,
+                           float* d_out, int ncols, uint32_t idesc, int nk, uint32_t a_lbo,
+                           uint32_t a_sbo, uint32_t a_layout, uint32_t a_kstep, uint32_t b_lbo,
+                           uint32_t b_sbo, uint32_t b_layout, uint32_t b_kstep, int nk_inner,
+                           uint32_t a_kstep2, uint32_t b_kstep2, cudaStream_t stream);
 
 /* ---- RoPE + QK RMSNorm + paged KV-cache store (the producer of the cache layout attention reads) --
  * replaces reference src/rope/rope.h:15-25 (rope_norm_store_kv_async) and :27-38

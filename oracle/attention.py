@@ -139,4 +139,5 @@ def decode_fp8_kpertoken(q, kcache, vcache, block_ids, kv_lens_total, q_scale, k
 
 
 # synthetic input builders: live in synth/ (neutral code), re-exported for the tests
-from synth.decode import make_decode_fp8_inputs, make_decode_fp8_kpt_inputs  # noqa: E402,F401
+from synth.decode import (make_decode_bf16_inputs, make_decode_fp8_inputs,  # noqa: E402,F401
+                          make_decode_fp8_kpt_inputs)

@@ -110,3 +110,37 @@ def make_decode_fp8_kpt_inputs(num_batch, num_seq_q, kv_lens_total, num_head_kv,
     return dict(q=q8, q_scale=q_scale.float(), kvcache=kvcache, kcache=kcache, vcache=vcache,
                 k_scale=k_scale, v_scale=v_scale, block_ids=block_ids.to(dev),
                 kv_lens_total=kv_lens_total.to(dev))
+
+
+def make_decode_bf16_inputs(num_batch, num_seq_q, kv_lens_total, num_head_kv, num_head_q,
+                            head_dim=128, block_size=64, seed=41, layout="NHD", device="cpu",
+                            extra_blocks=8, q_std=1.5):
+    """Seeded inputs for BF16 paged decode (shapes of reference tests/test_attention_decode_bf16.py:
+    77-160; q is drawn wider than there so that the softmax is not close to uniform and an error in
+    the scores is visible in the output). kv_lens_total includes the num_seq_q new tokens; unused
+    slots of each request's last block are zero (API contract, reference hpc/attention.py:364)."""
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    kv_lens_total = torch.as_tensor(kv_lens_total, dtype=torch.int32).cpu()
+    nblocks = (kv_lens_total + block_size - 1) // block_size
+    total_blocks = int(nblocks.sum())
+    num_blocks = int(total_blocks * 1.2) + num_batch + extra_blocks
+
+    q = (torch.randn((num_batch * num_seq_q, num_head_q, head_dim), generator=gen, device=dev)
+         * q_std).to(torch.bfloat16)
+    kvcache = torch.randn((num_blocks, 2, block_size, num_head_kv, head_dim), generator=gen,
+                          device=dev).to(torch.bfloat16)
+    perm = torch.randperm(num_blocks, generator=gen, device=dev)[:total_blocks].to(torch.int32).cpu()
+    block_ids = torch.zeros((num_batch, int(nblocks.max())), dtype=torch.int32)
+    cu = 0
+    for i in range(num_batch):
+        nb = int(nblocks[i])
+        block_ids[i, :nb] = perm[cu:cu + nb]
+        cu += nb
+        tail = int(kv_lens_total[i]) % block_size
+        if tail:
+            kvcache[int(block_ids[i, nb - 1]), :, tail:] = 0
+    if layout == "HND":
+        kvcache = kvcache.permute(0, 1, 3, 2, 4).contiguous().permute(0, 1, 3, 2, 4)
+    return dict(q=q, kvcache=kvcache, block_ids=block_ids.to(dev),
+                kv_lens_total=kv_lens_total.to(dev))

@@ -107,6 +107,25 @@ def rope_case(tag, num_req, is_prefill, mtp, hq, hkv, policy, seed):
     print("wrote rope", tag, q.shape)
 
 
+def decode_bf16_case(tag, num_batch, num_seq_q, kv_lens, hkv, hq, block_size, seed, layout):
+    """head-dim-128 bf16 decode: the reference's own ref function (tests/test_attention_decode_bf16.py:15)."""
+    fn = extract(REF / "tests/test_attention_decode_bf16.py", "ref_attn_with_paged_kvcache_func")
+    d = oa.make_decode_bf16_inputs(num_batch, num_seq_q, kv_lens, hkv, hq, block_size=block_size,
+                                   seed=seed, layout=layout, extra_blocks=2)
+    lens = d["kv_lens_total"]
+    nblocks = (lens + block_size - 1) // block_size
+    seqlenq = torch.full((num_batch,), num_seq_q, dtype=torch.int32)
+    kdummy = torch.empty(num_batch * num_seq_q, hkv, 128)
+    gt = fn(d["q"], kdummy, kdummy, d["kvcache"], d["block_ids"], nblocks, seqlenq, None,
+            lens - num_seq_q)
+    np.savez_compressed(
+        OUT / f"decode_bf16_{tag}.npz", q=_bf16_bits(d["q"]), kvcache=_bf16_bits(d["kvcache"].contiguous()),
+        block_ids=d["block_ids"].numpy(), kv_lens_total=lens.numpy(), out=gt.float().numpy(),
+        meta=np.array([num_batch, num_seq_q, hkv, hq, 128, block_size]),
+        layout=np.array([0 if layout == "NHD" else 1]))
+    print("wrote decode_bf16", tag, gt.shape)
+
+
 def decode_bf16_c1():
     """BASELINE config 0: test_attention_decode_bf16 bs=2 h=4 d=64 seq=128 on the torch CPU path."""
     fn = extract(REF / "tests/test_attention_decode_bf16.py", "ref_attn_with_paged_kvcache_func")
@@ -311,4 +330,6 @@ if __name__ == "__main__":
     rope_case("prefill_p2", 3, True, None, 4, 1, 2, 1)
     rope_case("decode_p1", 5, False, 1, 8, 2, 1, 2)
     decode_bf16_c1()
+    decode_bf16_case("b3_bs16_nhd", 3, 2, [70, 129, 300], 1, 8, 16, 41, "NHD")
+    decode_bf16_case("b4_bs64_hnd", 4, 1, [1, 64, 65, 260], 2, 8, 64, 10086, "HND")
     taskmap_cases()

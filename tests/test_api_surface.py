@@ -12,7 +12,7 @@ import torch
 REF = Path("/root/reference")
 
 IN_SCOPE_OPS = [
-    "assign_attention_decode_task", "attention_decode_fp8",
+    "assign_attention_decode_task", "attention_decode_fp8", "attention_decode_bf16",
     "attention_with_kvcache_blocksparse_prefill_fp8", "attention_with_kvcache_prefill_fp8",
     "fuse_moe", "fuse_moe_pertensor_fp8", "fuse_moe_blockwise", "fuse_moe_blockwise_fp8",
     "count_and_gather", "reduce",
@@ -25,7 +25,7 @@ IN_SCOPE_OPS = [
 ]
 
 PUBLIC_FUNCS = [
-    "QuantType", "assign_attention_decode_task", "attention_decode_fp8",
+    "QuantType", "assign_attention_decode_task", "attention_decode_fp8", "attention_decode_bf16",
     "attention_with_kvcache_blocksparse_prefill_fp8", "attention_with_kvcache_prefill_fp8",
     "get_attention_decode_task_workspace",
     "print_attention_decode_task",
@@ -82,4 +82,4 @@ def test_schemas_match_reference(hpc):
         want = _canon("hpc::" + ref[name])
         assert mine == want, f"{name}:\n  mine {mine}\n  ref  {want}"
         checked += 1
-    assert checked >= 19
+    assert checked >= 20

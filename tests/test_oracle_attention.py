@@ -60,6 +60,28 @@ def test_decode_bf16_config_c1_cpu_plumbing():
     assert torch.allclose(out.float(), torch.from_numpy(z["out"]), atol=0.016)
 
 
+def load_bf16_decode(name):
+    z = np.load(G / name)
+    B, sq, hkv, hq, D, bs = map(int, z["meta"])
+    kv = torch.from_numpy(z["kvcache"]).view(torch.bfloat16)
+    if int(z["layout"][0]) == 1:
+        kv = kv.permute(0, 1, 3, 2, 4).contiguous().permute(0, 1, 3, 2, 4)
+    d = dict(q=torch.from_numpy(z["q"]).view(torch.bfloat16), kvcache=kv,
+             block_ids=torch.from_numpy(z["block_ids"]),
+             kv_lens_total=torch.from_numpy(z["kv_lens_total"]))
+    return z, d, (B, sq, hkv, hq, D, bs)
+
+
+def test_decode_bf16_dim128_oracle_matches_reference_goldens():
+    """Head dim 128, page sizes 16 and 64, MTP: bit-equal to the reference's own test function."""
+    for name in ("decode_bf16_b3_bs16_nhd.npz", "decode_bf16_b4_bs64_hnd.npz"):
+        z, d, (B, sq, hkv, hq, D, bs) = load_bf16_decode(name)
+        out = oa.decode_bf16(d["q"], d["kvcache"][:, 0], d["kvcache"][:, 1], d["block_ids"],
+                             d["kv_lens_total"], sq)
+        ref = torch.from_numpy(z["out"])
+        assert torch.equal(out.float(), ref), (name, (out.float() - ref).abs().max())
+
+
 def test_input_builder_respects_zero_tail_contract():
     d = oa.make_decode_fp8_inputs(3, 2, [5, 64, 70], 2, 8, seed=3)
     kv = d["kvcache"].view(torch.uint8)
