@@ -129,14 +129,23 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int ntpc1 = p.task_map[0];
   const int* bin = p.task_map + (1 + static_cast<long long>(blockIdx.x) * ntpc1) * kTaskStride;
+  // rotated walk (decode_common.cuh): every role derives the same segment sequence
+  constexpr bool kRotate = RL <= 16;  // the carried softmax state costs 3 RL registers
+  const int u0 = (kRotate && p.rotate) ? walk_start(p.task_map, blockIdx.x) : 0;
+  const BinWalk walk = scan_bin(bin, ntpc1 - 1, u0, lane);
+  const int nseg = num_segments(walk);
 
   if (warp == 0) {
     // =========================== TMA producer ===========================================
-    const uint64_t pol_stream = make_policy_evict_first();
+    const uint64_t pol_stream = p.kv_policy == 0 ? make_policy_evict_first()
+                                : p.kv_policy == 1 ? make_policy_evict_normal()
+                                                   : make_policy_evict_last();
     uint32_t n = 0;      // global tile counter of this CTA
     uint32_t qcnt = 0;   // task counter for the Q double buffer
     Task t;
-    for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+    for (int j = 0; j < nseg; j++) {
+      const Segment sg = segment_of(walk, j);
+      if (!load_task(bin + static_cast<long long>(sg.row) * kTaskStride, t)) break;
       // The whole warp walks the task list with warp-uniform values and ONE elected lane issues:
       // operands of TMA / mbarrier instructions live in uniform registers, and values the compiler
       // cannot prove uniform (anything loaded from memory) would make it wrap each instruction in an
@@ -158,12 +167,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int nblk = (t.num_seqkv + kPage - 1) / kPage;
       const int* ids = p.block_ids + static_cast<long long>(t.ibatch) * p.num_seq_max_blocks +
                        t.iseq_start / kPage;
-      const int ntiles = t.num_tile_kv;
+      const int ntiles = sg.te < 0 ? t.num_tile_kv : sg.te;  // tiles [sg.tb, ntiles) of the task
       const int kc1 = p.k_head_first ? t.ihead_kv : 0;
       const int kc2 = p.k_head_first ? 0 : t.ihead_kv;
       const int vc1 = p.v_head_first ? t.ihead_kv : 0;
       const int vc2 = p.v_head_first ? 0 : t.ihead_kv;
-      for (int g0 = 0; g0 < ntiles; g0 += 16) {
+      for (int g0 = sg.tb; g0 < ntiles; g0 += 16) {
         int bi = g0 * 2 + lane;
         bi = bi < nblk ? bi : nblk - 1;  // a missing 2nd page of the last tile re-reads the 1st
         const int my_id = __ldg(ids + bi);
@@ -230,12 +239,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t n = 0;
       uint32_t qcnt = 0;
       Task t;
-      for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+      for (int j = 0; j < nseg; j++) {
+        const Segment sg = segment_of(walk, j);
+        if (!load_task(bin + static_cast<long long>(sg.row) * kTaskStride, t)) break;
         const int qb = qcnt & 1;
         mbar_wait(&q_full[qb], (qcnt >> 1) & 1);
         const uint64_t bd = qdesc0 + static_cast<uint64_t>(qb * (4096 >> 4));
-        const int ntiles = __shfl_sync(0xffffffffu, t.num_tile_kv, 0);
-        for (int tt = 0; tt < ntiles; tt++) {
+        const int ntiles = sg.te < 0 ? __shfl_sync(0xffffffffu, t.num_tile_kv, 0) : sg.te;
+        for (int tt = sg.tb; tt < ntiles; tt++) {
           const uint32_t st = n % kNumStages;
           const uint32_t buf = n & 1;
           mbar_wait(&k_full[st], (n / kNumStages) & 1);
@@ -270,7 +281,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     uint32_t n = 0;
     Task t;
-    for (const int* row = bin; load_task(row, t); row += kTaskStride) {
+    // online-softmax state of the task the rotated walk started inside of, kept from its first
+    // part (tail tiles) to its second part (head tiles) at the end of the walk
+    float carry_m[kRotate ? RL : 1], carry_l[kRotate ? RL : 1], carry_acc[kRotate ? RL : 1];
+    for (int j = 0; j < nseg; j++) {
+      const Segment sg = segment_of(walk, j);
+      if (!load_task(bin + static_cast<long long>(sg.row) * kTaskStride, t)) break;
       float c[RL], mrun[RL], lrun[RL], alpha_pend[RL];
       float acc[RL];
       {
@@ -289,10 +305,21 @@ __global__ void __launch_bounds__(kThreads, 1)
           alpha_pend[r] = 1.f;
           acc[r] = 0.f;
         }
+        if constexpr (kRotate) {
+          if (sg.restore) {
+#pragma unroll
+            for (int r = 0; r < RL; r++) {
+              mrun[r] = carry_m[r];
+              lrun[r] = carry_l[r];
+              acc[r] = carry_acc[r];
+            }
+          }
+        }
       }
       const int lim_len = t.num_seqkv;
       const int lim_causal = t.num_seqkvcache;
-      const int ntiles = t.num_tile_kv;
+      const int tile_begin = sg.tb;
+      const int ntiles = sg.te < 0 ? t.num_tile_kv : sg.te;  // tiles [tile_begin, ntiles)
       // k-per-token: this thread's key of tile tt sits in page (2 tt + row / 64) of the task's
       // page list; its scale is fetched one tile ahead
       const int* page_ids = p.block_ids + static_cast<long long>(t.ibatch) * p.num_seq_max_blocks +
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       float ks_next = 1.f;
       if constexpr (kKPerToken) {
         out_scale = __ldg(p.vscale + t.ihead_kv) * (1.0f / 256.0f);
-        ks_next = ntiles > 0 ? key_scale(0) : 0.f;
+        ks_next = ntiles > tile_begin ? key_scale(tile_begin) : 0.f;
       }
 
       auto consume_o = [&](uint32_t m) {
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       };
 
-      for (int tt = 0; tt < ntiles; tt++) {
+      for (int tt = tile_begin; tt < ntiles; tt++) {
         const uint32_t buf = n & 1;
         const uint32_t ph = (n >> 1) & 1;
         const float ks_cur = ks_next;
@@ -409,12 +436,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[buf]);
 
-        if (tt > 0) consume_o(n - 1);
+        if (tt > tile_begin) consume_o(n - 1);
 #pragma unroll
         for (int r = 0; r < RL; r++) alpha_pend[r] = x[r];
         n++;
       }
-      if (ntiles > 0) consume_o(n - 1);
+      if (ntiles > tile_begin) consume_o(n - 1);
+
+      if constexpr (kRotate) {
+        if (sg.save) {  // first part of the split task: its head tiles come last
+#pragma unroll
+          for (int r = 0; r < RL; r++) {
+            carry_m[r] = mrun[r];
+            carry_l[r] = lrun[r];
+            carry_acc[r] = acc[r];
+          }
+          continue;
+        }
+      }
 
       // ---- task epilogue: 1/sum, v scale, partial O and LSE out ----
       float* red = smax;  // reuse: [4 warps][32]
@@ -639,6 +678,16 @@ static int decode_fp8_impl(
     return HPC_OK;
   }
 
+  // Rotated bin walk: for token-major caches whose rows of neighbouring heads are neighbours in
+  // memory (pairs of 128-byte runs inside 256-byte-aligned lines). HPC_B200_DECODE_ROTATE=0 disables.
+  bool rotate = num_head_k >= 2 && (num_head_k % 2) == 0 && rows <= 16 &&
+                kcache_head_stride == 128 && vcache_head_stride == 128 &&
+                (kcache_token_stride % 256) == 0 && (vcache_token_stride % 256) == 0 &&
+                (kcache_block_stride % 256) == 0 && (vcache_block_stride % 256) == 0 &&
+                (reinterpret_cast<uintptr_t>(kcache_ptr) % 256) == 0 &&
+                (reinterpret_cast<uintptr_t>(vcache_ptr) % 256) == 0;
+  if (const char* e = getenv("HPC_B200_DECODE_ROTATE")) rotate = rotate && atoi(e) != 0;
+
   CUtensorMap tq, tk, tv;
   {
     uint64_t dims[3] = {128, static_cast<uint64_t>(num_head_q),
@@ -679,8 +728,11 @@ static int decode_fp8_impl(
     // L2 promotion must not exceed the contiguous run of one head's row: with token rows of
     // 128 B strided by Hkv*128 B (NHD) a 256 B promotion drags in the neighbouring head's row,
     // which is consumed by another CTA much later (measured: +49 % DRAM reads, profiles/).
-    CUtensorMapL2promotion promo = (tok_stride == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                                       : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    // ... unless the walk is rotated: then the neighbouring head's row is wanted by another CTA at
+    // the same time and the wider fetch is its prefetch (decode_common.cuh).
+    CUtensorMapL2promotion promo = (tok_stride == 128 || rotate)
+                                       ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (const char* e = getenv("HPC_B200_KV_PROMO")) {  // tuning knob: 0 none, 1 64B, 2 128B, 3 256B
       const int v = atoi(e);
       promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
@@ -725,6 +777,12 @@ static int decode_fp8_impl(
   p.ks_blk = kcache_block_stride / 4;
   p.ks_row = kcache_token_stride / 4;
   p.ks_head = kcache_head_stride / 4;
+  p.rotate = rotate ? 1 : 0;
+  // streamed once: evict_first - except under the rotated walk, where the promoted half of a line
+  // is another CTA's data a moment later and should not be the first thing to go (measured at C2:
+  // 180 vs 199 us, profiles/r2_decode_rotate_ab2.json)
+  p.kv_policy = rotate ? 1 : 0;
+  if (const char* e = getenv("HPC_B200_KV_POLICY")) p.kv_policy = atoi(e);  // tuning knob
 
   const int grid = splitk;  // == num_total_ctas of the task map
   int rc;

@@ -331,6 +331,10 @@ __global__ void __launch_bounds__(kThreads)
       task_map[0] = P + 1;
       task_map[1] = num_total_ctas;
       task_map[5] = m;
+      // tiles per kv head on the task line (rotated bin walk, decode_common.cuh). A pad word of the
+      // reference's header; the packed host map of the CPU scheduler leaves it zero like the
+      // reference, hpc/attention.py writes it when it splices a host map into the workspace.
+      task_map[6] = tot_tiles;
     }
   }
 }

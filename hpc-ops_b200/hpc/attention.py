@@ -559,6 +559,11 @@ def assign_attention_decode_task(
         task_map[:8].copy_(host[:8], non_blocking=True)
         task_map[20:24].copy_(host[20:24], non_blocking=True)
         task_map[48 : host.numel()].copy_(host[48:], non_blocking=True)
+        # header int 6 (a pad word in the reference): tiles per kv head, as the device scheduler
+        # writes it; the decode kernels rotate their bin walk by it (csrc/decode_common.cuh)
+        ns = num_seq_kvcache.to(torch.int64) + (0 if new_kv_included else int(mtp))
+        tiles = int(((ns + _TILE_N - 1) // _TILE_N).sum())
+        task_map[24:28].copy_(torch.tensor([tiles], dtype=torch.int32).view(torch.int8))
         return task_map
     return torch.ops.hpc.assign_attention_decode_task(
         num_seq_kvcache, num_head_kv, mtp, new_kv_included, min_process_len, task_map
