@@ -3,6 +3,7 @@
 Implemented in this build (sm_100a):
   * attention_decode_fp8            — quant_type QPERTOKEN_PERHEAD_KPERTENSOR_VPERTENSOR and
                                       QPERTOKEN_PERHEAD_KPERTOKEN_PERHEAD_VPERHEAD (in-cache k scales)
+  * attention_decode_bf16           — pages of 16 / 32 / 64 tokens, mtp 0..4
   * attention_with_kvcache_blocksparse_prefill_fp8 / attention_with_kvcache_prefill_fp8 (dense)
   * get_attention_decode_task_workspace / assign_attention_decode_task (CPU and CUDA)
   * print_attention_decode_task
